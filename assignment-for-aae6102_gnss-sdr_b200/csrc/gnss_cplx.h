@@ -1,0 +1,128 @@
+// gnss_cplx.h -- complex helpers, compile-time loops and compile-time twiddles.
+//
+// Everything here is `GNSS_HD`: it compiles as __host__ __device__ under nvcc
+// and as plain inline C++17 under g++.  The g++ build exists only so the
+// engine's index arithmetic can be exercised by the CPU test-suite
+// (tests/emu/); the product path is the CUDA build.
+#pragma once
+#include <cstdint>
+#include <type_traits>
+
+#if defined(__CUDACC__)
+#define GNSS_HD __host__ __device__ __forceinline__
+#else
+#define GNSS_HD inline
+#endif
+
+namespace gnss {
+
+struct alignas(8) cf {
+    float x, y;
+};
+
+GNSS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+GNSS_HD cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
+GNSS_HD cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+GNSS_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+GNSS_HD float cnorm(cf a) { return a.x * a.x + a.y * a.y; }
+// read-only global load of one complex value (LDG.E.64.CONSTANT on the device)
+GNSS_HD cf ld_ro(const cf* p) {
+#if defined(__CUDA_ARCH__)
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return mk(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+
+// ---- compile-time loop: f(std::integral_constant<int, I>) for I in [B, E) ----
+template <int B, int E, class F>
+GNSS_HD void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// ---- compile-time trigonometry (double Taylor series on a reduced argument) ----
+namespace detail {
+constexpr double kPi = 3.14159265358979323846264338327950288;
+// sin/cos of 2*pi*num/den, |result| exact to ~1e-16; octant symmetries are
+// resolved in integer arithmetic so special angles come out exact.
+constexpr double taylor_sin(double x) {   // |x| <= pi/4
+    double term = x, sum = x, x2 = x * x;
+    for (int i = 1; i < 12; ++i) { term *= -x2 / ((2 * i) * (2 * i + 1)); sum += term; }
+    return sum;
+}
+constexpr double taylor_cos(double x) {
+    double term = 1.0, sum = 1.0, x2 = x * x;
+    for (int i = 1; i < 12; ++i) { term *= -x2 / ((2 * i - 1) * (2 * i)); sum += term; }
+    return sum;
+}
+struct sc { double s, c; };
+constexpr sc sincos_turn(long long num, long long den) {   // angle = 2*pi*num/den
+    num %= den; if (num < 0) num += den;
+    // work in eighths of a turn: t = num/den in [0,1); octant o = floor(8t)
+    long long o = (8 * num) / den;
+    long long rnum = 8 * num - o * den;            // remainder/ (8 den) of a turn, in [0, den)
+    // angle inside the octant: phi = 2*pi * rnum / (8 den) in [0, pi/4)
+    double phi = 2.0 * kPi * (double)rnum / (8.0 * (double)den);
+    double s = taylor_sin(phi), c = taylor_cos(phi);
+    if (rnum == 0) { s = 0.0; c = 1.0; }
+    // rotate by o * 45 degrees
+    constexpr double h = 0.70710678118654752440084436210484903928;
+    double s1 = 0, c1 = 0;
+    switch (o) {
+        case 0: s1 = s; c1 = c; break;
+        case 1: s1 = h * (s + c); c1 = h * (c - s); break;
+        case 2: s1 = c; c1 = -s; break;
+        case 3: s1 = h * (c - s); c1 = -h * (c + s); break;
+        case 4: s1 = -s; c1 = -c; break;
+        case 5: s1 = -h * (s + c); c1 = h * (s - c); break;
+        case 6: s1 = -c; c1 = s; break;
+        default: s1 = h * (s - c); c1 = h * (c + s); break;
+    }
+    return sc{s1, c1};
+}
+}  // namespace detail
+
+// cos / sin of 2*pi*NUM/DEN as float compile-time constants.
+template <int NUM, int DEN>
+struct Tw {
+    static constexpr float c = (float)detail::sincos_turn(NUM, DEN).c;
+    static constexpr float s = (float)detail::sincos_turn(NUM, DEN).s;
+};
+
+// v * exp(-2*pi*i*NUM/DEN)  (forward-transform twiddle), special-casing 1/8 turns.
+template <int NUM, int DEN>
+GNSS_HD cf mul_tw(cf v) {
+    constexpr int T = ((NUM % DEN) + DEN) % DEN;
+    if constexpr (T == 0) {
+        return v;
+    } else if constexpr (4 * T == DEN) {          // -i
+        return mk(v.y, -v.x);
+    } else if constexpr (2 * T == DEN) {          // -1
+        return mk(-v.x, -v.y);
+    } else if constexpr (4 * T == 3 * DEN) {      // +i
+        return mk(-v.y, v.x);
+    } else if constexpr (8 * T == DEN) {          // (1-i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return mk((v.x + v.y) * h, (v.y - v.x) * h);
+    } else if constexpr (8 * T == 3 * DEN) {      // (-1-i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return mk((v.y - v.x) * h, -(v.x + v.y) * h);
+    } else {
+        constexpr float c = Tw<T, DEN>::c, s = Tw<T, DEN>::s;
+        return mk(v.x * c + v.y * s, v.y * c - v.x * s);
+    }
+}
+
+// ---- small compile-time integer helpers ----
+constexpr int cmodinv(int a, int m) {
+    a %= m;
+    for (int x = 1; x < m; ++x)
+        if ((a * x) % m == 1) return x;
+    return 0;
+}
+
+}  // namespace gnss

@@ -1,0 +1,281 @@
+// gnss_engine.h -- the N = 16 * 125 * Q prime-factor FFT engine, one task per call.
+//
+// N = samples per ms (signal.Sample): 58 000 = 16*125*29, 26 000 = 16*125*13.
+// 16, 125 and Q are pairwise coprime, so the N-point DFT is a twiddle-free 3-D
+// DFT (Good-Thomas).  With the input index mapped by the "Good" map
+//      n = (a*M1 + b*M2 + c*M3) mod N,          M1 = N/16, M2 = N/125, M3 = N/Q
+// and the output index by the CRT map (m mod 16, m mod 125, m mod Q) = (a',b',c'):
+//      Y[a',b',c'] = sum_{a,b,c} Z[a,b,c] W16^(a a') W125^(b b') WQ^(c c').
+//
+// A unit (one N-point transform) is spread over a thread-block cluster of R
+// CTAs; CTA r keeps rows a in [r*16/R, (r+1)*16/R) of the [16][Q][125] array in
+// shared memory ("D buffer", layout [a_local][c][pos]).  Four passes:
+//   pass1  load (functor) + DFT-Q over c          task = (a_local, b)
+//   pass2  125 = 5 x 25 : DFT-5 over b1 + W125    task = (row, b2),  b = 25 b1 + b2
+//   pass3  DFT-25 over b2                         task = (row, k1);  pos 25 k1 + k2 holds b' = k1 + 5 k2
+//   pass4  DFT-16 over a, columns split over the R CTAs; reads the other CTAs'
+//          D buffers through distributed shared memory; store functor
+//          (|.|^2 accumulate for the search, spectrum store for K0/K1)
+// The functions below do ONE task each and take the thread's task index, so the
+// same code runs under the CUDA kernels (gnss_kernels.cu) and under the CPU
+// emulation used by the test-suite (tests/emu/).
+//
+// Replaces the arithmetic of acquisition.m:56-59 (fft / ifft built-ins).
+#pragma once
+#include "gnss_radix.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+#include <cmath>
+#endif
+
+namespace gnss {
+
+template <int Q>
+struct Geo {
+    static constexpr int N = 2000 * Q;
+    static constexpr int ROW = 125 * Q;           // columns (c', pos) per a-row
+    static constexpr int M1 = 125 * Q, M2 = 16 * Q, M3 = 2000;
+    static constexpr int INV1 = cmodinv(M1 % 16, 16);
+    static constexpr int INV2 = cmodinv(M2 % 125, 125);
+    static constexpr int INV3 = cmodinv(M3 % Q, Q);
+    static constexpr int E1 = M1 * INV1, E2 = M2 * INV2, E3 = M3 * INV3;   // CRT idempotents (< N each)
+    static_assert(Q % 2 == 1 && Q % 5 != 0, "Q must be coprime to 2000");
+    static_assert(INV1 && INV2 && INV3, "no modular inverse");
+
+    GNSS_HD static int good(int a, int b, int c) { return (a * M1 + b * M2 + c * M3) % N; }
+    GNSS_HD static int crt(int a, int b, int c) { return (a * E1 + b * E2 + c * E3) % N; }
+    // storage index of Good coordinates (a,b,c) in a spectrum held in "G layout" [16][Q][125]
+    GNSS_HD static int gidx(int a, int b, int c) { return (a * Q + c) * 125 + b; }
+    // column id (c', pos) -> b' (pos = 25*k1 + k2 holds b' = k1 + 5*k2)
+    GNSS_HD static int bprime_of_pos(int pos) { return pos / 25 + 5 * (pos % 25); }
+    GNSS_HD static int pos_of_bprime(int bp) { return 25 * (bp % 5) + bp / 5; }
+    // output lag / frequency index of (a', column)
+    GNSS_HD static int lag_of(int ap, int col) {
+        const int cp = col / 125, pos = col - cp * 125;
+        return crt(ap, bprime_of_pos(pos), cp);
+    }
+    // Good coordinates of frequency index (k - s): shift amounts per axis
+    GNSS_HD static void shift_coords(int s, int& sa, int& sb, int& sc) {
+        int sm = s % N; if (sm < 0) sm += N;
+        sa = (int)(((long long)sm * INV1) % 16);
+        sb = (int)(((long long)sm * INV2) % 125);
+        sc = (int)(((long long)sm * INV3) % Q);
+    }
+    GNSS_HD static void cell_of_lag(int m, int& ap, int& col) {
+        ap = m & 15;
+        col = (m % Q) * 125 + pos_of_bprime(m % 125);
+    }
+};
+
+template <int Q, int R>
+struct Split {
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "cluster size");
+    static constexpr int A = 16 / R;                       // a-rows per CTA
+    static constexpr int ROW = Geo<Q>::ROW;
+    static constexpr int CH = (ROW + R - 1) / R;           // pass-4 columns per CTA
+    static constexpr int D_ELEMS = A * ROW;                // cf per CTA
+    static constexpr int ACC_ELEMS = 16 * CH;              // floats per CTA
+    static constexpr int P1_TASKS = A * 125;
+    static constexpr int P2_TASKS = A * Q * 25;
+    static constexpr int P3_TASKS = A * Q * 5;
+    static constexpr int P4_TASKS = CH;
+};
+
+// ------------------------------------------------------------------ pass 1
+template <int Q, int R, class Loader>
+GNSS_HD void pass1_task(int task, int rank, const Loader& ld, cf* __restrict__ D) {
+    using S = Split<Q, R>;
+    const int al = task / 125, b = task - al * 125;
+    const int a = rank * S::A + al;
+    cf z[Q];
+    ld.template load<Q>(a, b, z);
+    dft_odd<Q>(z);
+    cf* dst = D + (al * Q) * 125 + b;
+    static_for<0, Q>([&](auto cc) {
+        constexpr int C = decltype(cc)::value;
+        dst[C * 125] = z[C];
+    });
+}
+
+// ------------------------------------------------------------------ pass 2
+// tw125[j] = exp(-2*pi*i*j/125), j in [0,125)
+template <int Q, int R>
+GNSS_HD void pass2_task(int task, cf* __restrict__ D, const cf* __restrict__ tw125) {
+    const int row = task / 25, b2 = task - row * 25;
+    cf* p = D + row * 125 + b2;
+    cf u[5] = {p[0], p[25], p[50], p[75], p[100]};
+    dft_odd<5>(u);
+    p[0] = u[0];
+    static_for<1, 5>([&](auto kc) {
+        constexpr int K1 = decltype(kc)::value;
+        p[25 * K1] = cmul(u[K1], tw125[b2 * K1]);
+    });
+}
+
+// ------------------------------------------------------------------ pass 3
+template <int Q, int R>
+GNSS_HD void pass3_task(int task, cf* __restrict__ D) {
+    cf* p = D + task * 25;            // task = row*5 + k1  ->  offset row*125 + 25*k1
+    cf v[25];
+    static_for<0, 25>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        v[I] = p[I];
+    });
+    dft25(v);                          // v[5*q1+q2] = X[q1 + 5*q2]
+    static_for<0, 25>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;       // output index k2 = I
+        p[I] = v[5 * (I % 5) + I / 5];
+    });
+}
+
+// ------------------------------------------------------------------ pass 4
+// Dall[r] = D buffer of cluster CTA r (DSMEM-mapped on the GPU).
+template <int Q, int R, class Storer>
+GNSS_HD void pass4_task(int t, int rank, cf* const* Dall, Storer& st) {
+    using S = Split<Q, R>;
+    const int col = rank * S::CH + t;
+    if (t >= S::CH || col >= S::ROW) return;
+    cf w[16];
+    static_for<0, 16>([&](auto ac) {
+        constexpr int Aidx = decltype(ac)::value;
+        w[Aidx] = Dall[Aidx / S::A][(Aidx % S::A) * S::ROW + col];
+    });
+    dft16(w);                          // w[4*k1+k2] = Y[a' = k1 + 4*k2]
+    st.template store<Q, R>(col, t, w);
+}
+
+// ================================================================== functors
+// ---- search (K2): Z = Cc * X_base[k - s], accumulate |Y|^2 ----
+struct SearchLoader {
+    const cf* __restrict__ cc;      // conj(fft(code))/N of this PRN, G layout
+    const cf* __restrict__ x;       // fft(wiped-off block) of this (base, block), G layout
+    int sa, sb, sc;                 // bin shift in Good coordinates
+    template <int Q>
+    GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
+        const int as = (a - sa) & 15;
+        int bs = b - sb; if (bs < 0) bs += 125;
+        const cf* pc = cc + (a * Q) * 125 + b;
+        const cf* px = x + (as * Q) * 125 + bs;
+        int cs = (sc == 0) ? 0 : Q - sc;             // (0 - sc) mod Q
+        static_for<0, Q>([&](auto c_) {
+            constexpr int C = decltype(c_)::value;
+            const cf cv = ld_ro(pc + C * 125);
+            const cf xv = ld_ro(px + cs * 125);
+            z[C] = cmul(cv, xv);
+            cs = (cs + 1 == Q) ? 0 : cs + 1;
+        });
+    }
+};
+
+struct PowerAccumStorer {
+    float* __restrict__ acc;        // [16][CH] floats of this CTA
+    template <int Q, int R>
+    GNSS_HD void store(int /*col*/, int t, const cf (&w)[16]) {
+        constexpr int CH = Split<Q, R>::CH;
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;               // w[I], I = 4*k1 + k2
+            constexpr int AP = (I / 4) + 4 * (I % 4);            // a' = k1 + 4*k2
+            acc[AP * CH + t] += cnorm(w[I]);
+        });
+    }
+};
+
+// ---- spectrum store (K0 / K1): write Y to global in G layout of the *next* transform ----
+struct SpectrumStorer {
+    cf* __restrict__ out;
+    float scale;                    // 1 for K1, 1/N for K0
+    int conj;                       // 1 for K0 (store conj(fft(code))/N)
+    template <int Q, int R>
+    GNSS_HD void store(int col, int /*t*/, const cf (&w)[16]) {
+        using G = Geo<Q>;
+        const int cp = col / 125, pos = col - cp * 125;
+        const int bp = G::bprime_of_pos(pos);
+        const int bg = (bp * G::INV2) % 125, cg = (cp * G::INV3) % Q;
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int AP = (I / 4) + 4 * (I % 4);
+            constexpr int AG = (AP * G::INV1) % 16;
+            cf v = w[I];
+            v.x *= scale;
+            v.y *= conj ? -scale : scale;
+            out[G::gidx(AG, bg, cg)] = v;
+        });
+    }
+};
+
+// ---- code replica loader (K0): real +-1 samples, natural order ----
+struct CodeLoader {
+    const int8_t* __restrict__ scode;   // N samples of this PRN (acquisition.m:51)
+    template <int Q>
+    GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
+        static_for<0, Q>([&](auto c_) {
+            constexpr int C = decltype(c_)::value;
+            z[C] = mk((float)scode[Geo<Q>::good(a, b, C)], 0.f);
+        });
+    }
+};
+
+// ---- wipe-off loader (K1): acquisition.m:43,56 with exact phase, plus the M-ms fold (A.8) ----
+GNSS_HD void carrier_sincos(double f_hz, double fs_hz, long long n1 /*1-based sample index*/,
+                            float& co, float& si) {
+    // cycles = f*(n)/Fs ; f*n is exact in double for integer-Hz f (|f*n| < 2^53)
+    const double cyc = (f_hz * (double)n1) / fs_hz;
+    const double fr = cyc - floor(cyc);                  // [0,1)
+#if defined(__CUDA_ARCH__)
+    sincospif((float)(2.0 * fr), &si, &co);
+#else
+    const double ang = 2.0 * 3.14159265358979323846 * fr;
+    co = (float)cos(ang);
+    si = (float)sin(ang);
+#endif
+}
+
+struct WipeoffLoader {
+    const void* __restrict__ raw;   // start of this coherent block (sample 0 of the block)
+    int data_type;                  // 1 real, 2 I/Q          (file.dataType)
+    int precision;                  // 1 int8, 2 int16        (file.dataPrecision)
+    int coh_ms;                     // M
+    double f_hz, fs_hz;             // IF + doppler of this base, Fs
+    float mean_i, mean_q;           // int16 path only (acquisition.m:32)
+    template <int Q>
+    GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
+        constexpr int N = Geo<Q>::N;
+        static_for<0, Q>([&](auto c_) {
+            constexpr int C = decltype(c_)::value;
+            const int n = Geo<Q>::good(a, b, C);
+            float ax = 0.f, ay = 0.f;
+            for (int j = 0; j < coh_ms; ++j) {
+                const long long idx = (long long)j * N + n;
+                float xi, xq;
+                if (precision == 2) {
+                    const int16_t* p = (const int16_t*)raw;
+                    xi = (float)p[2 * idx] - mean_i;
+                    xq = (float)p[2 * idx + 1] - mean_q;
+                } else if (data_type == 2) {
+                    const int8_t* p = (const int8_t*)raw;
+                    xi = (float)p[2 * idx];
+                    xq = (float)p[2 * idx + 1];
+                } else {
+                    xi = (float)((const int8_t*)raw)[idx];
+                    xq = 0.f;
+                }
+                float co, si;
+                carrier_sincos(f_hz, fs_hz, idx + 1, co, si);
+                ax += xi * co - xq * si;
+                ay += xi * si + xq * co;
+            }
+            z[C] = mk(ax, ay);
+        });
+    }
+};
+
+// ================================================================== row-end helpers
+struct RowPeak {
+    float peak;        // max accumulated power
+    int lag;           // first lag attaining it
+};
+GNSS_HD bool peak_better(float v, int m, float bv, int bm) { return v > bv || (v == bv && m < bm); }
+
+}  // namespace gnss

@@ -1,0 +1,95 @@
+// gnss_radix.h -- register-resident forward DFT butterflies (exp(-2*pi*i*nk/R)).
+//
+//   dft_odd<Q>   any odd length (5, 13, 29, ...): symmetric-pair form, all
+//                coefficients compile-time immediates, 2H + H(4H+4) FP ops, H=(Q-1)/2
+//   dft4, dft16  16 = 4 x 4 Cooley-Tukey
+//   dft25        25 = 5 x 5 Cooley-Tukey
+//
+// dft16 / dft25 leave their result digit-reversed: v[R1*k1 + k2] = X[k1 + R1*k2]
+// (R1 = 4 resp. 5); callers index accordingly, which costs nothing because all
+// register indices are static.
+#pragma once
+#include "gnss_cplx.h"
+
+namespace gnss {
+
+template <int Q>
+GNSS_HD void dft_odd(cf (&v)[Q]) {
+    static_assert(Q % 2 == 1 && Q >= 3, "odd length");
+    constexpr int H = (Q - 1) / 2;
+    cf a[H + 1], b[H + 1];
+    const cf x0 = v[0];
+    cf s0 = x0;
+    static_for<1, H + 1>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        a[J] = cadd(v[J], v[Q - J]);
+        b[J] = csub(v[J], v[Q - J]);
+        s0 = cadd(s0, a[J]);
+    });
+    v[0] = s0;
+    static_for<1, H + 1>([&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        float cx = x0.x, cy = x0.y, sx = 0.f, sy = 0.f;
+        static_for<1, H + 1>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            constexpr int T = (J * K) % Q;
+            constexpr float c = Tw<T, Q>::c, s = Tw<T, Q>::s;
+            cx += c * a[J].x;
+            cy += c * a[J].y;
+            sx += s * b[J].x;
+            sy += s * b[J].y;
+        });
+        // X[K] = C - i S ; X[Q-K] = C + i S
+        v[K] = mk(cx + sy, cy - sx);
+        v[Q - K] = mk(cx - sy, cy + sx);
+    });
+}
+
+GNSS_HD void dft4(cf& x0, cf& x1, cf& x2, cf& x3) {
+    const cf t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    x1 = mk(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
+    x3 = mk(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+}
+
+// in: v[4*n1 + n2] = x[4*n1 + n2]; out: v[4*k1 + k2] = X[k1 + 4*k2]
+GNSS_HD void dft16(cf (&v)[16]) {
+    static_for<0, 4>([&](auto n2c) {
+        constexpr int N2 = decltype(n2c)::value;
+        dft4(v[N2], v[4 + N2], v[8 + N2], v[12 + N2]);     // over n1 -> k1 at v[4*k1 + N2]
+        static_for<1, 4>([&](auto k1c) {
+            constexpr int K1 = decltype(k1c)::value;
+            v[4 * K1 + N2] = mul_tw<N2 * K1, 16>(v[4 * K1 + N2]);
+        });
+    });
+    static_for<0, 4>([&](auto k1c) {
+        constexpr int K1 = decltype(k1c)::value;
+        dft4(v[4 * K1], v[4 * K1 + 1], v[4 * K1 + 2], v[4 * K1 + 3]);   // over n2 -> k2
+    });
+}
+
+// in: v[5*n1 + n2]; out: v[5*k1 + k2] = X[k1 + 5*k2]
+GNSS_HD void dft25(cf (&v)[25]) {
+    static_for<0, 5>([&](auto n2c) {
+        constexpr int N2 = decltype(n2c)::value;
+        cf u[5] = {v[N2], v[5 + N2], v[10 + N2], v[15 + N2], v[20 + N2]};
+        dft_odd<5>(u);
+        v[N2] = u[0];
+        static_for<1, 5>([&](auto k1c) {
+            constexpr int K1 = decltype(k1c)::value;
+            v[5 * K1 + N2] = mul_tw<N2 * K1, 25>(u[K1]);
+        });
+    });
+    static_for<0, 5>([&](auto k1c) {
+        constexpr int K1 = decltype(k1c)::value;
+        cf u[5] = {v[5 * K1], v[5 * K1 + 1], v[5 * K1 + 2], v[5 * K1 + 3], v[5 * K1 + 4]};
+        dft_odd<5>(u);
+        static_for<0, 5>([&](auto k2c) {
+            constexpr int K2 = decltype(k2c)::value;
+            v[5 * K1 + K2] = u[K2];
+        });
+    });
+}
+
+}  // namespace gnss
