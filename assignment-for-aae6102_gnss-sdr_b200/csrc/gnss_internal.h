@@ -1,0 +1,65 @@
+// gnss_internal.h -- argument blocks shared by the kernels (per-Q translation units)
+// and the C-ABI host code (gnssacq.cu).  Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include "gnss_engine.h"
+
+namespace gnss {
+
+// One (PRN, Doppler-bin) row's outcome, written by the search kernel (K2 + K3).
+struct Candidate {
+    float peak;        // max over lags of the non-coherent power (acquisition.m:63 restricted to the row)
+    int lag;           // first lag attaining it (0-based)
+    double sum_all;    // sum over all lags of power^2
+    double sum_win;    // sum of power^2 over lags lag-(w-1) .. lag+(w-1), clipped to [0,N-1] (acquisition.m:67)
+};
+
+struct SearchArgs {
+    const cf* cc;          // [P][N]   conj(fft(code))/N, G layout
+    const cf* x;           // [n_bases][K][N] forward spectra of wiped-off blocks, G layout
+    const int* bin_base;   // [B] which base a bin derives from
+    const int* bin_shift;  // [B] shift in FFT bins relative to that base
+    int P, B, K;
+    int w;                 // ceil(Fs/fc) (acquisition.m:66)
+    Candidate* cand;       // [P][B]
+    float* surface;        // optional [P][B][N] (debug), lag order
+};
+
+struct WipeArgs {
+    const void* raw;       // device IF block
+    int data_type, precision, coh_ms, K;
+    size_t block_bytes;    // bytes per coherent block
+    const double* base_freq_hz;   // [n_bases] IF + doppler of each base
+    double fs_hz;
+    const double* means;   // [2] int16 path (device), else nullptr
+    cf* x;                 // [n_bases][K][N]
+};
+
+struct CodeArgs {
+    const int8_t* scode;   // [P][N] upsampled +-1 code replicas (acquisition.m:51)
+    cf* cc;                // [P][N]
+};
+
+struct NaturalArgs {
+    const cf* in;          // [units][N] natural order
+    cf* out;               // [units][N] natural order
+};
+
+struct VariantOps {
+    int Q, R, T;
+    size_t smem_search, smem_transform;
+    cudaError_t (*prepare)();
+    cudaError_t (*launch_code)(const CodeArgs&, int units, cudaStream_t);
+    cudaError_t (*launch_wipe)(const WipeArgs&, int units, cudaStream_t);
+    cudaError_t (*launch_natural)(const NaturalArgs&, int units, cudaStream_t);
+    cudaError_t (*launch_search)(const SearchArgs&, int rows, cudaStream_t);
+};
+
+// defined in gnss_q3.cu / gnss_q13.cu / gnss_q29.cu
+const VariantOps* gnss_variants_q3(int* count);
+const VariantOps* gnss_variants_q13(int* count);
+const VariantOps* gnss_variants_q29(int* count);
+
+}  // namespace gnss

@@ -1,0 +1,315 @@
+// gnss_kernels.cuh -- sm_100a kernels around the engine passes (gnss_engine.h).
+//
+//   code_kernel    K0  fft(code replica) -> conj(.)/N, G layout          (acquisition.m:58, once per handle)
+//   wipe_kernel    K1  wipe-off (+ M-ms fold) + forward FFT per (base, block)   (acquisition.m:56-57)
+//   search_kernel  K2  per (PRN, bin) row: for each of the K blocks multiply the two spectra in the
+//                      load stage, transform, |.|^2, accumulate on chip; then K3 = row peak, first-index
+//                      argmax, sum of squares and windowed sum of squares   (acquisition.m:59,62-63,67)
+//   natural_kernel     plain forward DFT (test hook)
+//
+// One transform = one thread-block cluster of R CTAs; each CTA keeps 16/R rows of the
+// [16][Q][125] prime-factor array in shared memory, pass 4 pulls the other CTAs' rows through
+// distributed shared memory (cluster.map_shared_rank).  The non-coherent accumulator of a row
+// (N floats) lives in shared memory, split over the cluster, for the whole K loop: HBM/L2 only
+// ever sees the two input spectra and one 24-byte candidate per row.
+#pragma once
+#include <cooperative_groups.h>
+#include <climits>
+#include "gnss_internal.h"
+
+namespace gnss {
+namespace cg = cooperative_groups;
+
+struct NaturalLoader {
+    const cf* __restrict__ in;
+    template <int Q>
+    __device__ __forceinline__ void load(int a, int b, cf (&z)[Q]) const {
+        static_for<0, Q>([&](auto c_) {
+            constexpr int C = decltype(c_)::value;
+            z[C] = in[Geo<Q>::good(a, b, C)];
+        });
+    }
+};
+struct NaturalStorer {
+    cf* __restrict__ out;
+    template <int Q, int R>
+    __device__ __forceinline__ void store(int col, int, const cf (&w)[16]) {
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int AP = (I / 4) + 4 * (I % 4);
+            out[Geo<Q>::lag_of(AP, col)] = w[I];
+        });
+    }
+};
+
+struct RedScratch {
+    float wv[32];
+    int wm[32];
+    double ws[32];
+    // this CTA's slot, read by the other CTAs of the cluster
+    float peak; int lag; double sum_all; double sum_win;
+    // cluster-wide winner, broadcast inside the CTA
+    float g_peak; int g_lag;
+};
+
+template <int Q, int R>
+struct Smem {
+    using S = Split<Q, R>;
+    static constexpr size_t d_bytes = (size_t)S::D_ELEMS * sizeof(cf);
+    static constexpr size_t acc_bytes = (size_t)S::ACC_ELEMS * sizeof(float);
+    static constexpr size_t tw_bytes = 125 * sizeof(cf);
+    static constexpr size_t red_bytes = ((sizeof(RedScratch) + 15) / 16) * 16;
+    static constexpr size_t transform = d_bytes + tw_bytes;
+    static constexpr size_t search = d_bytes + acc_bytes + tw_bytes + red_bytes;
+};
+
+__device__ __forceinline__ void fill_tw125(cf* tw, int tid, int T) {
+    for (int j = tid; j < 125; j += T) {
+        double s, c;
+        sincospi(-2.0 * (double)j / 125.0, &s, &c);
+        tw[j] = mk((float)c, (float)s);
+    }
+}
+
+// (value, first index) max + double sum over the CTA; result valid in thread 0.
+template <int T>
+__device__ __forceinline__ void block_reduce(float& v, int& m, double& s, RedScratch* rs) {
+    constexpr unsigned full = 0xffffffffu;
+    constexpr int NW = T / 32;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const float ov = __shfl_down_sync(full, v, off);
+        const int om = __shfl_down_sync(full, m, off);
+        const double os = __shfl_down_sync(full, s, off);
+        if (peak_better(ov, om, v, m)) { v = ov; m = om; }
+        s += os;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { rs->wv[warp] = v; rs->wm[warp] = m; rs->ws[warp] = s; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < NW ? rs->wv[lane] : -1.f;
+        m = lane < NW ? rs->wm[lane] : INT_MAX;
+        s = lane < NW ? rs->ws[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const float ov = __shfl_down_sync(full, v, off);
+            const int om = __shfl_down_sync(full, m, off);
+            const double os = __shfl_down_sync(full, s, off);
+            if (peak_better(ov, om, v, m)) { v = ov; m = om; }
+            s += os;
+        }
+    }
+    __syncthreads();
+}
+
+// passes 1-4 of one transform; cluster-wide barriers around the DSMEM pass
+template <int Q, int R, int T, class Loader, class Storer>
+__device__ __forceinline__ void unit_device(const Loader& ld, Storer& st, cf* D, cf* const* Dall,
+                                            const cf* tw, cg::cluster_group& cluster, int rank, int tid) {
+    using S = Split<Q, R>;
+    for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+    __syncthreads();
+    for (int t = tid; t < S::P2_TASKS; t += T) pass2_task<Q, R>(t, D, tw);
+    __syncthreads();
+    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+    for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
+    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+}
+
+#define GNSS_KERNEL_PROLOGUE                                                     \
+    using S = Split<Q, R>;                                                       \
+    using G = Geo<Q>;                                                            \
+    (void)sizeof(G);                                                             \
+    cg::cluster_group cluster = cg::this_cluster();                              \
+    const int tid = threadIdx.x;                                                 \
+    const int rank = (R > 1) ? (int)cluster.block_rank() : 0;                    \
+    const int unit = blockIdx.x / R;                                             \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                    \
+    cf* D = reinterpret_cast<cf*>(smem_raw);                                     \
+    cf* Dall[R];                                                                 \
+    _Pragma("unroll") for (int r = 0; r < R; ++r)                                \
+        Dall[r] = (R > 1) ? cluster.map_shared_rank(D, r) : D;
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) code_kernel(CodeArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    cf* tw = D + S::D_ELEMS;
+    fill_tw125(tw, tid, T);
+    __syncthreads();
+    CodeLoader ld{a.scode + (size_t)unit * G::N};
+    SpectrumStorer st{a.cc + (size_t)unit * G::N, 1.0f / (float)G::N, 1};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+}
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) wipe_kernel(WipeArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    cf* tw = D + S::D_ELEMS;
+    fill_tw125(tw, tid, T);
+    __syncthreads();
+    const int base = unit / a.K, k = unit - base * a.K;
+    WipeoffLoader ld;
+    ld.raw = (const unsigned char*)a.raw + (size_t)k * a.block_bytes;
+    ld.data_type = a.data_type;
+    ld.precision = a.precision;
+    ld.coh_ms = a.coh_ms;
+    ld.f_hz = a.base_freq_hz[base];
+    ld.fs_hz = a.fs_hz;
+    ld.mean_i = a.means ? (float)a.means[0] : 0.f;
+    ld.mean_q = a.means ? (float)a.means[1] : 0.f;
+    SpectrumStorer st{a.x + (size_t)unit * G::N, 1.0f, 0};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+}
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    cf* tw = D + S::D_ELEMS;
+    fill_tw125(tw, tid, T);
+    __syncthreads();
+    NaturalLoader ld{a.in + (size_t)unit * G::N};
+    NaturalStorer st{a.out + (size_t)unit * G::N};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+}
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
+    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    const int row = unit;                       // row = bin * P + prn_index (PRN fastest: rows in
+    const int p = row % a.P, b = row / a.P;     // flight share the same forward spectra in L2)
+
+    fill_tw125(tw, tid, T);
+    for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+    __syncthreads();
+
+    int sa, sb, sc;
+    G::shift_coords(a.bin_shift[b], sa, sb, sc);
+    const cf* ccp = a.cc + (size_t)p * G::N;
+    const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::N;
+    PowerAccumStorer st{acc};
+    for (int k = 0; k < a.K; ++k) {
+        SearchLoader ld{ccp, xb + (size_t)k * G::N, sa, sb, sc};
+        unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+    }
+
+    // ---- K3: row peak (first index on ties), sum of squares, windowed sum of squares ----
+    float bv = -1.f;
+    int bm = INT_MAX;
+    double ss = 0.0;
+    for (int e = tid; e < S::ACC_ELEMS; e += T) {
+        const int ap = e / S::CH, t = e - ap * S::CH;
+        const int col = rank * S::CH + t;
+        if (col < S::ROW) {
+            const float v = acc[e];
+            const int m = G::lag_of(ap, col);
+            if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
+            ss += (double)v * (double)v;
+            if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
+        }
+    }
+    block_reduce<T>(bv, bm, ss, rs);
+    if (tid == 0) { rs->peak = bv; rs->lag = bm; rs->sum_all = ss; }
+    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+    if (tid == 0) {
+        float gv = -1.f;
+        int gm = INT_MAX;
+        for (int r = 0; r < R; ++r) {
+            const RedScratch* o = (R > 1) ? cluster.map_shared_rank(rs, r) : rs;
+            const float ov = o->peak;
+            const int om = o->lag;
+            if (peak_better(ov, om, gv, gm)) { gv = ov; gm = om; }
+        }
+        rs->g_peak = gv;
+        rs->g_lag = gm;
+    }
+    __syncthreads();
+    const int gm = rs->g_lag;
+    double wsum = 0.0;
+    for (int i = tid; i < 2 * a.w - 1; i += T) {
+        const int m = gm - (a.w - 1) + i;
+        if (m >= 0 && m < G::N) {
+            int ap, col;
+            G::cell_of_lag(m, ap, col);
+            if (col / S::CH == rank) {
+                const float v = acc[ap * S::CH + (col - rank * S::CH)];
+                wsum += (double)v * (double)v;
+            }
+        }
+    }
+    float dv = -1.f;
+    int dm = INT_MAX;
+    block_reduce<T>(dv, dm, wsum, rs);
+    if (tid == 0) rs->sum_win = wsum;
+    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+    if (rank == 0 && tid == 0) {
+        double s_all = 0.0, s_win = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const RedScratch* o = (R > 1) ? cluster.map_shared_rank(rs, r) : rs;
+            s_all += o->sum_all;
+            s_win += o->sum_win;
+        }
+        Candidate c;
+        c.peak = rs->g_peak;
+        c.lag = rs->g_lag;
+        c.sum_all = s_all;
+        c.sum_win = s_win;
+        a.cand[(size_t)p * a.B + b] = c;
+    }
+    if constexpr (R > 1) cluster.sync();   // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+// ------------------------------------------------------------------ launch glue
+template <class K, class A>
+static cudaError_t launch_clustered(K kern, const A& args, int units, int R, int T, size_t smem, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * R), 1, 1);
+    cfg.blockDim = dim3((unsigned)T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)R;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    A copy = args;
+    return cudaLaunchKernelEx(&cfg, kern, copy);
+}
+
+template <int Q, int R, int T, int MINB>
+struct Variant {
+    static cudaError_t prepare() {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(code_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wipe_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(natural_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(search_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
+    }
+    static cudaError_t launch_code(const CodeArgs& a, int units, cudaStream_t s) {
+        return launch_clustered(code_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+    }
+    static cudaError_t launch_wipe(const WipeArgs& a, int units, cudaStream_t s) {
+        return launch_clustered(wipe_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+    }
+    static cudaError_t launch_natural(const NaturalArgs& a, int units, cudaStream_t s) {
+        return launch_clustered(natural_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+    }
+    static cudaError_t launch_search(const SearchArgs& a, int rows, cudaStream_t s) {
+        return launch_clustered(search_kernel<Q, R, T, MINB>, a, rows, R, T, Smem<Q, R>::search, s);
+    }
+    static constexpr VariantOps ops() {
+        return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, R>::transform,
+                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_search};
+    }
+};
+
+}  // namespace gnss

@@ -1,0 +1,523 @@
+// gnssacq.cu -- C-ABI host side of libgnssacq.so (include/gnssacq.h).
+//
+// Owns: config validation, the C/A code tables (generateCAcode.m, acquisition.m:50-51), the
+// HBM-resident cache of conj(fft(code))/N, pinned IF staging, the Doppler-bin -> (base, shift)
+// plan, kernel sequencing on one stream, and K4 (per-PRN winner, noise floor, SNR,
+// threshold: acquisition.m:62-70).  No CPU fallback: every numeric step of the search runs in the
+// sm_100a kernels of gnss_kernels.cuh.
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gnssacq.h"
+#include "gnss_internal.h"
+
+using namespace gnss;
+
+#define GNSSACQ_VERSION_STR "gnssacq 0.1.0 (sm_100a)"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------- C/A code (generateCAcode.m)
+const int kG2Delay[51] = {5,   6,   7,   8,   17,  18,  139, 140, 141, 251, 252, 254, 255, 256, 257, 258, 469,
+                          470, 471, 472, 473, 474, 509, 512, 513, 514, 515, 516, 859, 860, 861, 862, 145, 175,
+                          52,  21,  237, 235, 886, 657, 634, 762, 355, 1012, 176, 603, 130, 359, 595, 68,  386};
+
+// Bit form of the +-1 registers: value -1 <-> bit 1 (product of -1s == XOR of bits).
+void ca_chips(int prn, int8_t* out) {
+    uint8_t g1[1023], g2[1023];
+    uint32_t r1 = 0x3ff, r2 = 0x3ff;   // stage k at bit (k-1); all ones == all -1 (generateCAcode.m:34,49)
+    for (int i = 0; i < 1023; ++i) {
+        g1[i] = (r1 >> 9) & 1;                                                    // output = stage 10
+        g2[i] = (r2 >> 9) & 1;
+        const uint32_t f1 = ((r1 >> 2) ^ (r1 >> 9)) & 1;                          // taps 3,10
+        const uint32_t f2 = ((r2 >> 1) ^ (r2 >> 2) ^ (r2 >> 5) ^ (r2 >> 7) ^ (r2 >> 8) ^ (r2 >> 9)) & 1;   // 2,3,6,8,9,10
+        r1 = ((r1 << 1) | f1) & 0x3ff;
+        r2 = ((r2 << 1) | f2) & 0x3ff;
+    }
+    const int d = kG2Delay[prn - 1];
+    for (int i = 0; i < 1023; ++i) {
+        const uint8_t g2d = g2[(i + 1023 - d) % 1023];        // g2 rotated right by d (generateCAcode.m:61)
+        // +-1 values: v = 1 - 2*bit ; CAcode = -(v1*v2) = -(1 - 2*(b1^b2))
+        out[i] = (int8_t)((g1[i] ^ g2d) ? 1 : -1);
+    }
+}
+
+// acquisition.m:50-51 -- scode(n) = [CA CA](ceil(n*(fc/Fs))), n = 1..N, ratio formed first, in double.
+void code_replica(const gnssacq_config& c, int prn, int8_t* out) {
+    int8_t ca[1023];
+    ca_chips(prn, ca);
+    const double ratio = c.code_hz / c.fs_hz;
+    for (int n = 1; n <= c.samples_per_ms; ++n) {
+        long idx = (long)std::ceil((double)n * ratio);    // 1-based into the doubled code
+        if (idx < 1) idx = 1;
+        out[n - 1] = ca[(idx - 1) % 1023];
+    }
+}
+
+// ---------------------------------------------------------------- small kernels
+// K4: acquisition.m:62-70 from the per-row candidates.
+__global__ void finalize_kernel(const Candidate* __restrict__ cand, int P, int B, int N, int w, double fmin,
+                                double fstep, double thr, const int* __restrict__ prn_ids,
+                                gnssacq_result* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const Candidate* row = cand + (size_t)p * B;
+    float g = -1.f;
+    for (int b = 0; b < B; ++b) g = fmaxf(g, row[b].peak);
+    int fbin = -1, cp = INT_MAX;
+    for (int b = 0; b < B; ++b) {
+        if (row[b].peak == g) {
+            if (fbin < 0) fbin = b;                     // first bin attaining the maximum (:62)
+            cp = min(cp, row[b].lag);                   // first code phase attaining it (:63)
+        }
+    }
+    if (fbin < 0) { fbin = 0; cp = 0; }
+    const Candidate c = row[fbin];
+    const int cp1 = cp + 1;                             // MATLAB's 1-based codePhase
+    const long long cnt = (long long)max(cp1 - w, 0) + (long long)max(N - cp1 - w + 1, 0);   // :67-68 index set
+    const double noise = (c.sum_all - c.sum_win) / (double)cnt;
+    const double pk = (double)g;
+    const double snr = 10.0 * log10(pk * pk / noise);
+    gnssacq_result r;
+    r.prn = prn_ids[p];
+    r.acquired = (snr >= thr) ? 1 : 0;                  // :70 (NaN compares false)
+    r.code_phase = cp;
+    r.doppler_bin = fbin;
+    r.doppler_hz = fmin + fstep * (double)fbin;         // :64
+    r.peak = pk;
+    r.noise_meansq = noise;
+    r.snr_db = snr;
+    r.fine_freq_hz = nan("");
+    out[p] = r;
+}
+
+// acquisition.m:30-32 -- per-component mean of the int16 I/Q block (exact integer sums).
+__global__ void sum_int16_kernel(const int16_t* __restrict__ s, long long n_pairs, long long* __restrict__ sums) {
+    long long si = 0, sq = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs;
+         i += (long long)gridDim.x * blockDim.x) {
+        si += s[2 * i];
+        sq += s[2 * i + 1];
+    }
+    for (int off = 16; off; off >>= 1) {
+        si += __shfl_down_sync(0xffffffffu, si, off);
+        sq += __shfl_down_sync(0xffffffffu, sq, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long*)&sums[0], (unsigned long long)si);
+        atomicAdd((unsigned long long*)&sums[1], (unsigned long long)sq);
+    }
+}
+__global__ void means_kernel(const long long* __restrict__ sums, long long n_pairs, double* __restrict__ means) {
+    means[0] = (double)sums[0] / (double)n_pairs;
+    means[1] = (double)sums[1] / (double)n_pairs;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- handle
+struct gnssacq_handle {
+    gnssacq_config cfg;
+    const VariantOps* ops = nullptr;
+    int device = 0;
+    int N = 0, P = 0, B = 0, K = 0, M = 0;
+    int w = 0;
+    size_t if_bytes = 0;
+    std::vector<int> bin_base, bin_shift;
+    std::vector<double> base_freq;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device buffers
+    void* d_if = nullptr;
+    int8_t* d_scode = nullptr;
+    cf* d_cc = nullptr;
+    cf* d_x = nullptr;
+    int *d_bin_base = nullptr, *d_bin_shift = nullptr, *d_prn = nullptr;
+    double* d_base_freq = nullptr;
+    Candidate* d_cand = nullptr;
+    gnssacq_result* d_res = nullptr;
+    float* d_surface = nullptr;
+    long long* d_sums = nullptr;
+    double* d_means = nullptr;
+    cf *d_fft_in = nullptr, *d_fft_out = nullptr;
+    // pinned host
+    void* h_if = nullptr;
+    gnssacq_result* h_res = nullptr;
+    cudaEvent_t ev[6] = {};
+    bool have_h2d = false;
+    int launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(gnssacq_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, GNSSACQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+const VariantOps* pick_variant(int Q, int R, int T) {
+    int n = 0;
+    const VariantOps* v = nullptr;
+    if (Q == 3) v = gnss_variants_q3(&n);
+    else if (Q == 13) v = gnss_variants_q13(&n);
+    else if (Q == 29) v = gnss_variants_q29(&n);
+    if (!v) return nullptr;
+    for (int i = 0; i < n; ++i)
+        if ((R == 0 || v[i].R == R) && (T == 0 || v[i].T == T)) return &v[i];
+    return nullptr;
+}
+
+// Doppler bins -> (base transform, shift in FFT bins): f_b = f_base + s * (Fs/N)   
+void plan_bins(gnssacq_handle* h) {
+    const gnssacq_config& c = h->cfg;
+    const double df = c.fs_hz / (double)c.samples_per_ms;
+    h->bin_base.assign(h->B, 0);
+    h->bin_shift.assign(h->B, 0);
+    h->base_freq.clear();
+    for (int b = 0; b < h->B; ++b) {
+        const double f = c.if_hz + (c.freq_min_hz + c.freq_step_hz * (double)b);     // acquisition.m:42-43
+        int found = -1, shift = 0;
+        for (size_t i = 0; i < h->base_freq.size(); ++i) {
+            const double r = (f - h->base_freq[i]) / df;
+            const double rr = std::nearbyint(r);
+            if (std::fabs(r - rr) * df < 1e-6 && std::fabs(rr) < (double)(c.samples_per_ms / 2)) {
+                found = (int)i;
+                shift = (int)rr;
+                break;
+            }
+        }
+        if (found < 0) {
+            h->base_freq.push_back(f);
+            found = (int)h->base_freq.size() - 1;
+            shift = 0;
+        }
+        h->bin_base[b] = found;
+        h->bin_shift[b] = shift;
+    }
+}
+
+int validate(const gnssacq_config* c, std::string& why) {
+    if (!c) { why = "cfg is NULL"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (!(c->fs_hz > 0) || !(c->code_hz > 0)) { why = "fs_hz and code_hz must be positive"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->data_type != 1 && c->data_type != 2) { why = "data_type must be 1 (real) or 2 (I/Q)"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->data_precision != 1 && c->data_precision != 2) { why = "data_precision must be 1 (int8) or 2 (int16)"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->data_precision == 2 && c->data_type != 2) { why = "int16 input is always I/Q (acquisition.m:29-32)"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->freq_num < 1 || c->noncoh_blocks < 1 || c->coh_ms < 1) { why = "freq_num, noncoh_blocks, coh_ms must be >= 1"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
+    for (int i = 0; i < c->n_prn; ++i)
+        if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
+        why = "samples_per_ms must be 2000*Q (built: Q = 3, 13, 29 -> 6000, 26000, 58000)";
+        return GNSSACQ_ERR_UNSUPPORTED_N;
+    }
+    return GNSSACQ_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* gnssacq_version(void) { return GNSSACQ_VERSION_STR; }
+
+int gnssacq_config_default(gnssacq_config* c) {
+    if (!c) return GNSSACQ_ERR_INVALID_ARG;
+    std::memset(c, 0, sizeof(*c));
+    c->fs_hz = 58e6;                 // initParameters.m:42
+    c->if_hz = 4.58e6;               // :41
+    c->code_hz = 1.023e6;            // :44
+    c->samples_per_ms = 58000;       // :46
+    c->data_type = 2;                // :37
+    c->data_precision = 1;           // :38
+    c->freq_min_hz = -10000.0;       // :52
+    c->freq_step_hz = 500.0;         // :51
+    c->freq_num = 41;                // :53
+    c->noncoh_blocks = 20;           // :54
+    c->coh_ms = 1;
+    c->n_prn = 32;                   // acquisition.m:47
+    for (int i = 0; i < 32; ++i) c->prn[i] = i + 1;
+    c->snr_threshold_db = 12.0;      // acquisition.m:70
+    c->device = -1;
+    return GNSSACQ_OK;
+}
+
+size_t gnssacq_if_bytes(const gnssacq_config* c) {
+    if (!c) return 0;
+    return (size_t)c->samples_per_ms * (size_t)c->data_type * (size_t)c->data_precision *
+           (size_t)c->noncoh_blocks * (size_t)c->coh_ms;
+}
+
+int gnssacq_ca_code(int32_t prn, int8_t out[1023]) {
+    if (!out || prn < 1 || prn > 51) return GNSSACQ_ERR_INVALID_ARG;
+    ca_chips(prn, out);
+    return GNSSACQ_OK;
+}
+
+int gnssacq_code_replica(const gnssacq_config* c, int32_t prn, int8_t* out) {
+    if (!c || !out || prn < 1 || prn > 51 || c->samples_per_ms <= 0 || !(c->fs_hz > 0)) return GNSSACQ_ERR_INVALID_ARG;
+    code_replica(*c, prn, out);
+    return GNSSACQ_OK;
+}
+
+const char* gnssacq_last_error(const gnssacq_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gnssacq_destroy(gnssacq_handle* h) {
+    if (!h) return GNSSACQ_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
+    cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
+    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
+    if (h->h_if) cudaFreeHost(h->h_if);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return GNSSACQ_OK;
+}
+
+int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
+    gnssacq_handle* h = nullptr;
+    if (!out) return fail(nullptr, GNSSACQ_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    std::string why;
+    int rc = validate(cfg, why);
+    if (rc != GNSSACQ_OK) return fail(nullptr, rc, why);
+
+    const int Q = cfg->samples_per_ms / 2000;
+    const VariantOps* ops = pick_variant(Q, cfg->cluster_ctas, cfg->threads);
+    if (!ops) {
+        char buf[200];
+        std::snprintf(buf, sizeof buf, "no engine variant for samples_per_ms=%d (Q=%d) cluster_ctas=%d threads=%d",
+                      cfg->samples_per_ms, Q, cfg->cluster_ctas, cfg->threads);
+        return fail(nullptr, GNSSACQ_ERR_UNSUPPORTED_N, buf);
+    }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, GNSSACQ_ERR_NO_DEVICE, "no CUDA device: libgnssacq has no CPU fallback");
+    }
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, GNSSACQ_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(nullptr, GNSSACQ_ERR_NO_DEVICE, "cannot query device");
+    if (prop.major != 10) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "device %d is sm_%d%d; libgnssacq is built for sm_100a only", dev, prop.major, prop.minor);
+        return fail(nullptr, GNSSACQ_ERR_NO_DEVICE, buf);
+    }
+
+    h = new (std::nothrow) gnssacq_handle();
+    if (!h) return fail(nullptr, GNSSACQ_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    h->ops = ops;
+    h->device = dev;
+    h->N = cfg->samples_per_ms;
+    h->P = cfg->n_prn;
+    h->B = cfg->freq_num;
+    h->K = cfg->noncoh_blocks;
+    h->M = cfg->coh_ms;
+    h->w = (int)std::ceil(cfg->fs_hz / cfg->code_hz);          // acquisition.m:66
+    h->if_bytes = gnssacq_if_bytes(cfg);
+    plan_bins(h);
+    const size_t N = (size_t)h->N;
+    const size_t nb = h->base_freq.size();
+
+#define CUC(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+            gnssacq_destroy(h);                                                                          \
+            return fail(nullptr, e__ == cudaErrorMemoryAllocation ? GNSSACQ_ERR_NOMEM : GNSSACQ_ERR_CUDA, m__); \
+        }                                                                                                \
+    } while (0)
+
+    CUC(cudaSetDevice(dev));
+    CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (auto& e : h->ev) CUC(cudaEventCreate(&e));
+    CUC(ops->prepare());
+    CUC(cudaMalloc(&h->d_if, h->if_bytes));
+    CUC(cudaMalloc(&h->d_scode, (size_t)h->P * N));
+    CUC(cudaMalloc(&h->d_cc, (size_t)h->P * N * sizeof(cf)));
+    CUC(cudaMalloc(&h->d_x, nb * (size_t)h->K * N * sizeof(cf)));
+    CUC(cudaMalloc(&h->d_bin_base, h->B * sizeof(int)));
+    CUC(cudaMalloc(&h->d_bin_shift, h->B * sizeof(int)));
+    CUC(cudaMalloc(&h->d_prn, h->P * sizeof(int)));
+    CUC(cudaMalloc(&h->d_base_freq, nb * sizeof(double)));
+    CUC(cudaMalloc(&h->d_cand, (size_t)h->P * h->B * sizeof(Candidate)));
+    CUC(cudaMalloc(&h->d_res, h->P * sizeof(gnssacq_result)));
+    CUC(cudaMalloc(&h->d_sums, 2 * sizeof(long long)));
+    CUC(cudaMalloc(&h->d_means, 2 * sizeof(double)));
+    if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
+    CUC(cudaMallocHost(&h->h_if, h->if_bytes));
+    CUC(cudaMallocHost(&h->h_res, h->P * sizeof(gnssacq_result)));
+    CUC(cudaMemcpy(h->d_bin_base, h->bin_base.data(), h->B * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(h->d_bin_shift, h->bin_shift.data(), h->B * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(h->d_prn, cfg->prn, h->P * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(h->d_base_freq, h->base_freq.data(), nb * sizeof(double), cudaMemcpyHostToDevice));
+
+    // code tables -> HBM, then K0 fills the conj-spectrum cache
+    {
+        std::vector<int8_t> sc((size_t)h->P * N);
+        for (int p = 0; p < h->P; ++p) code_replica(*cfg, cfg->prn[p], sc.data() + (size_t)p * N);
+        CUC(cudaMemcpy(h->d_scode, sc.data(), sc.size(), cudaMemcpyHostToDevice));
+        CodeArgs a{h->d_scode, h->d_cc};
+        CUC(ops->launch_code(a, h->P, h->stream));
+        CUC(cudaStreamSynchronize(h->stream));
+    }
+#undef CUC
+    *out = h;
+    return GNSSACQ_OK;
+}
+
+int gnssacq_set_stream(gnssacq_handle* h, void* s) {
+    if (!h) return GNSSACQ_ERR_INVALID_ARG;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return GNSSACQ_OK;
+}
+
+static int enqueue(gnssacq_handle* h, const void* d_if) {
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    CU(cudaEventRecord(h->ev[1], s));
+    const double* means = nullptr;
+    if (h->cfg.data_precision == 2) {
+        const long long pairs = (long long)h->N * h->K * h->M;
+        CU(cudaMemsetAsync(h->d_sums, 0, 2 * sizeof(long long), s));
+        sum_int16_kernel<<<296, 256, 0, s>>>((const int16_t*)d_if, pairs, h->d_sums);
+        means_kernel<<<1, 1, 0, s>>>(h->d_sums, pairs, h->d_means);
+        CU(cudaGetLastError());
+        h->launches += 2;
+        means = h->d_means;
+    }
+    WipeArgs wa;
+    wa.raw = d_if;
+    wa.data_type = h->cfg.data_type;
+    wa.precision = h->cfg.data_precision;
+    wa.coh_ms = h->M;
+    wa.K = h->K;
+    wa.block_bytes = (size_t)h->N * h->M * h->cfg.data_type * h->cfg.data_precision;
+    wa.base_freq_hz = h->d_base_freq;
+    wa.fs_hz = h->cfg.fs_hz;
+    wa.means = means;
+    wa.x = h->d_x;
+    CU(h->ops->launch_wipe(wa, (int)h->base_freq.size() * h->K, s));
+    h->launches += 1;
+    CU(cudaEventRecord(h->ev[2], s));
+    SearchArgs sa;
+    sa.cc = h->d_cc;
+    sa.x = h->d_x;
+    sa.bin_base = h->d_bin_base;
+    sa.bin_shift = h->d_bin_shift;
+    sa.P = h->P; sa.B = h->B; sa.K = h->K;
+    sa.w = h->w;
+    sa.cand = h->d_cand;
+    sa.surface = h->d_surface;
+    CU(h->ops->launch_search(sa, h->P * h->B, s));
+    h->launches += 1;
+    CU(cudaEventRecord(h->ev[3], s));
+    finalize_kernel<<<(h->P + 63) / 64, 64, 0, s>>>(h->d_cand, h->P, h->B, h->N, h->w, h->cfg.freq_min_hz,
+                                                    h->cfg.freq_step_hz, h->cfg.snr_threshold_db, h->d_prn, h->d_res);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    CU(cudaEventRecord(h->ev[4], s));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_enqueue_device(gnssacq_handle* h, const void* d_if, size_t nbytes) {
+    if (!h || !d_if) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (nbytes < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "IF block shorter than noncoh_blocks*coh_ms ms");
+    CU(cudaSetDevice(h->device));
+    h->have_h2d = false;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    return enqueue(h, d_if);
+}
+
+int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !out) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->h_res, h->d_res, h->P * sizeof(gnssacq_result), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->h_res, h->P * sizeof(gnssacq_result));
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        if (h->have_h2d) cudaEventElapsedTime(&st->h2d_ms, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&st->wipeoff_fft_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&st->search_ms, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&st->finalize_ms, h->ev[3], h->ev[4]);
+        cudaEventElapsedTime(&st->d2h_ms, h->ev[4], h->ev[5]);
+        cudaEventElapsedTime(&st->total_ms, h->ev[0], h->ev[5]);
+        st->kernel_launches = h->launches;
+        st->n_bases = (int)h->base_freq.size();
+        st->cluster_ctas = h->ops->R;
+        st->threads = h->ops->T;
+    }
+    return GNSSACQ_OK;
+}
+
+int gnssacq_search_device(gnssacq_handle* h, const void* d_if, size_t nbytes, gnssacq_result* out, gnssacq_stats* st) {
+    int rc = gnssacq_enqueue_device(h, d_if, nbytes);
+    if (rc != GNSSACQ_OK) return rc;
+    return gnssacq_fetch_results(h, out, st);
+}
+
+int gnssacq_search(gnssacq_handle* h, const void* if_samples, size_t nbytes, gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !if_samples || !out) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (nbytes < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "IF block shorter than noncoh_blocks*coh_ms ms");
+    CU(cudaSetDevice(h->device));
+    std::memcpy(h->h_if, if_samples, h->if_bytes);             // caller's buffer is free again after this
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(cudaMemcpyAsync(h->d_if, h->h_if, h->if_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->have_h2d = true;
+    int rc = enqueue(h, h->d_if);
+    if (rc != GNSSACQ_OK) return rc;
+    return gnssacq_fetch_results(h, out, st);
+}
+
+int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out) {
+    if (!h || !out || prn_index < 0 || prn_index >= h->P) return fail(h, GNSSACQ_ERR_INVALID_ARG, "bad argument");
+    if (!h->d_surface) return fail(h, GNSSACQ_ERR_STATE, "handle was created without keep_surface");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)h->B * h->N;
+    CU(cudaMemcpy(out, h->d_surface + (size_t)prn_index * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_fft_forward(gnssacq_handle* h, const float* in, float* out) {
+    if (!h || !in || !out) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->N * sizeof(cf);
+    if (!h->d_fft_in) {
+        CU(cudaMalloc(&h->d_fft_in, bytes));
+        CU(cudaMalloc(&h->d_fft_out, bytes));
+    }
+    CU(cudaMemcpyAsync(h->d_fft_in, in, bytes, cudaMemcpyHostToDevice, h->stream));
+    NaturalArgs a{h->d_fft_in, h->d_fft_out};
+    CU(h->ops->launch_natural(a, 1, h->stream));
+    CU(cudaMemcpyAsync(out, h->d_fft_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GNSSACQ_OK;
+}
+
+}  // extern "C"

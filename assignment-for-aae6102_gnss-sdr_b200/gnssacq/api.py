@@ -1,0 +1,233 @@
+"""ctypes binding of ``libgnssacq.so`` (``include/gnssacq.h``).
+
+This is the binding that is testable in the build image (no MATLAB/Octave
+here); ``matlab/gnssacq_mex.c`` binds the same entry points for MATLAB.
+There is no CPU fallback: if the shared library is missing, importing this
+module raises, and without a B200 ``gnssacq_create`` fails with
+``GNSSACQ_ERR_NO_DEVICE``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+GNSSACQ_MAX_PRN = 64
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnssacq.so")
+
+
+class GnssAcqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gnssacq error {code}: {msg}")
+        self.code = code
+
+
+STATUS = {
+    0: "GNSSACQ_OK", -1: "GNSSACQ_ERR_INVALID_ARG", -2: "GNSSACQ_ERR_UNSUPPORTED_N",
+    -3: "GNSSACQ_ERR_SHORT_BUFFER", -4: "GNSSACQ_ERR_CUDA", -5: "GNSSACQ_ERR_NO_DEVICE",
+    -6: "GNSSACQ_ERR_NOMEM", -7: "GNSSACQ_ERR_STATE",
+}
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("fs_hz", C.c_double), ("if_hz", C.c_double), ("code_hz", C.c_double),
+        ("samples_per_ms", C.c_int32), ("data_type", C.c_int32), ("data_precision", C.c_int32),
+        ("freq_min_hz", C.c_double), ("freq_step_hz", C.c_double), ("freq_num", C.c_int32),
+        ("noncoh_blocks", C.c_int32), ("coh_ms", C.c_int32),
+        ("n_prn", C.c_int32), ("prn", C.c_int32 * GNSSACQ_MAX_PRN),
+        ("snr_threshold_db", C.c_double),
+        ("device", C.c_int32), ("cluster_ctas", C.c_int32), ("threads", C.c_int32),
+        ("keep_surface", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("prn", C.c_int32), ("acquired", C.c_int32), ("code_phase", C.c_int32), ("doppler_bin", C.c_int32),
+        ("doppler_hz", C.c_double), ("peak", C.c_double), ("noise_meansq", C.c_double),
+        ("snr_db", C.c_double), ("fine_freq_hz", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float), ("wipeoff_fft_ms", C.c_float), ("search_ms", C.c_float),
+        ("finalize_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
+        ("kernel_launches", C.c_int32), ("n_bases", C.c_int32), ("cluster_ctas", C.c_int32),
+        ("threads", C.c_int32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = (
+    "gnssacq_version", "gnssacq_config_default", "gnssacq_if_bytes", "gnssacq_create",
+    "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
+    "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_fetch_results",
+    "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward",
+)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(nvcc, sm_100a).  gnssacq has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gnssacq_version.restype = C.c_char_p
+    lib.gnssacq_config_default.argtypes = [C.POINTER(Config)]
+    lib.gnssacq_if_bytes.argtypes = [C.POINTER(Config)]
+    lib.gnssacq_if_bytes.restype = C.c_size_t
+    lib.gnssacq_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.gnssacq_destroy.argtypes = [vp]
+    lib.gnssacq_last_error.argtypes = [vp]
+    lib.gnssacq_last_error.restype = C.c_char_p
+    lib.gnssacq_set_stream.argtypes = [vp, vp]
+    lib.gnssacq_search.argtypes = [vp, vp, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
+    lib.gnssacq_search_device.argtypes = [vp, vp, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
+    lib.gnssacq_enqueue_device.argtypes = [vp, vp, C.c_size_t]
+    lib.gnssacq_fetch_results.argtypes = [vp, C.POINTER(Result), C.POINTER(Stats)]
+    lib.gnssacq_ca_code.argtypes = [C.c_int32, vp]
+    lib.gnssacq_code_replica.argtypes = [C.POINTER(Config), C.c_int32, vp]
+    lib.gnssacq_read_surface.argtypes = [vp, C.c_int32, vp]
+    lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
+    return lib
+
+
+lib = _load()
+
+
+def version() -> str:
+    return lib.gnssacq_version().decode()
+
+
+def default_config() -> Config:
+    cfg = Config()
+    lib.gnssacq_config_default(C.byref(cfg))
+    return cfg
+
+
+def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Optional[int] = None,
+                data_type=2, data_precision=1, freq_min_hz=-10000.0, freq_step_hz=500.0,
+                freq_num: Optional[int] = None, noncoh_blocks=20, coh_ms=1,
+                prns: Sequence[int] = tuple(range(1, 33)), snr_threshold_db=12.0, device=-1,
+                cluster_ctas=0, threads=0, keep_surface=False) -> Config:
+    cfg = default_config()
+    cfg.fs_hz, cfg.if_hz, cfg.code_hz = fs_hz, if_hz, code_hz
+    cfg.samples_per_ms = int(samples_per_ms if samples_per_ms else np.ceil(fs_hz * 1e-3))
+    cfg.data_type, cfg.data_precision = data_type, data_precision
+    cfg.freq_min_hz, cfg.freq_step_hz = freq_min_hz, freq_step_hz
+    cfg.freq_num = int(freq_num if freq_num is not None else 2 * abs(freq_min_hz) / freq_step_hz + 1)
+    cfg.noncoh_blocks, cfg.coh_ms = noncoh_blocks, coh_ms
+    prns = list(prns)
+    if len(prns) > GNSSACQ_MAX_PRN:
+        raise ValueError("too many PRNs")
+    cfg.n_prn = len(prns)
+    for i in range(GNSSACQ_MAX_PRN):
+        cfg.prn[i] = prns[i] if i < len(prns) else 0
+    cfg.snr_threshold_db = snr_threshold_db
+    cfg.device, cfg.cluster_ctas, cfg.threads = device, cluster_ctas, threads
+    cfg.keep_surface = int(bool(keep_surface))
+    return cfg
+
+
+def ca_code(prn: int) -> np.ndarray:
+    out = np.zeros(1023, dtype=np.int8)
+    rc = lib.gnssacq_ca_code(prn, out.ctypes.data)
+    if rc:
+        raise GnssAcqError(rc, STATUS.get(rc, "?"))
+    return out
+
+
+def code_replica(cfg: Config, prn: int) -> np.ndarray:
+    out = np.zeros(cfg.samples_per_ms, dtype=np.int8)
+    rc = lib.gnssacq_code_replica(C.byref(cfg), prn, out.ctypes.data)
+    if rc:
+        raise GnssAcqError(rc, STATUS.get(rc, "?"))
+    return out
+
+
+class Searcher:
+    """Owns one ``gnssacq_handle`` (one GPU, one PRN shard)."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = lib.gnssacq_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise GnssAcqError(rc, (lib.gnssacq_last_error(None) or b"").decode())
+        self.if_bytes = int(lib.gnssacq_if_bytes(C.byref(cfg)))
+        self.last_stats: Optional[Stats] = None
+
+    def close(self) -> None:
+        if self._h:
+            lib.gnssacq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise GnssAcqError(rc, (lib.gnssacq_last_error(self._h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(lib.gnssacq_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def search(self, if_bytes) -> List[Result]:
+        """Host buffer in (bytes / bytearray / numpy int8|int16), result rows out."""
+        buf = np.frombuffer(if_bytes, dtype=np.uint8) if not isinstance(if_bytes, np.ndarray) else if_bytes
+        buf = np.ascontiguousarray(buf)
+        out = (Result * self.cfg.n_prn)()
+        st = Stats()
+        self._check(lib.gnssacq_search(self._h, buf.ctypes.data, buf.nbytes, out, C.byref(st)))
+        self.last_stats = st
+        return list(out)
+
+    def search_device(self, dev_ptr: int, nbytes: int) -> List[Result]:
+        out = (Result * self.cfg.n_prn)()
+        st = Stats()
+        self._check(lib.gnssacq_search_device(self._h, C.c_void_p(dev_ptr), nbytes, out, C.byref(st)))
+        self.last_stats = st
+        return list(out)
+
+    def enqueue_device(self, dev_ptr: int, nbytes: int) -> None:
+        self._check(lib.gnssacq_enqueue_device(self._h, C.c_void_p(dev_ptr), nbytes))
+
+    def fetch(self) -> List[Result]:
+        out = (Result * self.cfg.n_prn)()
+        st = Stats()
+        self._check(lib.gnssacq_fetch_results(self._h, out, C.byref(st)))
+        self.last_stats = st
+        return list(out)
+
+    def read_surface(self, prn_index: int) -> np.ndarray:
+        out = np.empty((self.cfg.freq_num, self.cfg.samples_per_ms), dtype=np.float32)
+        self._check(lib.gnssacq_read_surface(self._h, prn_index, out.ctypes.data))
+        return out
+
+    def fft_forward(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        if x.size != self.cfg.samples_per_ms:
+            raise ValueError("length must equal samples_per_ms")
+        out = np.empty_like(x)
+        self._check(lib.gnssacq_fft_forward(self._h, x.ctypes.data, out.ctypes.data))
+        return out

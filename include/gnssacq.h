@@ -1,0 +1,142 @@
+/* gnssacq.h -- C ABI of libgnssacq.so: B200-native GPS L1 C/A parallel code-phase acquisition.
+ *
+ * Drop-in boundary for ONE function of the reference receiver,
+ *     Acquired = acquisition(file, signal, acq)
+ *     (SDR_MATLAB-main/acqtckpos/acquisition.m:1, coarse search :19-80),
+ * which has no FFI of its own (it is a MATLAB function).  The entry points below
+ * are what a MEX gateway (matlab/gnssacq_mex.c) or a ctypes loader
+ * (gnssacq/api.py) binds; INTEGRATION.md shows both stubs.
+ *
+ * Conventions: plain C, no C++ or torch types; every function returns 0 on
+ * success or a negative gnssacq_status; no exceptions or exit() cross the ABI.
+ * A handle is not re-entrant; distinct handles may be used from distinct
+ * threads.  Caller owns `if_samples` and `out`; the library copies the input
+ * into its own pinned staging before the call returns.  There is NO CPU
+ * fallback: without a CUDA device (sm_100) gnssacq_create fails with
+ * GNSSACQ_ERR_NO_DEVICE.
+ */
+#ifndef GNSSACQ_H_
+#define GNSSACQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNSSACQ_MAX_PRN 64
+
+typedef enum gnssacq_status {
+    GNSSACQ_OK = 0,
+    GNSSACQ_ERR_INVALID_ARG = -1,    /* NULL pointer, non-positive count, PRN outside 1..51 ...        */
+    GNSSACQ_ERR_UNSUPPORTED_N = -2,  /* samples_per_ms is not 2000*Q with Q in the built set           */
+    GNSSACQ_ERR_SHORT_BUFFER = -3,   /* fewer IF bytes than noncoh_blocks*coh_ms ms                    */
+    GNSSACQ_ERR_CUDA = -4,           /* a CUDA runtime call failed; see gnssacq_last_error             */
+    GNSSACQ_ERR_NO_DEVICE = -5,      /* no CUDA device / wrong architecture                            */
+    GNSSACQ_ERR_NOMEM = -6,
+    GNSSACQ_ERR_STATE = -7           /* e.g. gnssacq_read_surface without keep_surface                 */
+} gnssacq_status;
+
+/* Mirrors exactly the fields acquisition.m reads (acquisition.m:24-43,53,66,70) plus the
+ * extensions BASELINE.json's configs need (coh_ms, PRN shard, engine variant). */
+typedef struct gnssacq_config {
+    double fs_hz;             /* signal.Fs            (initParameters.m:42) */
+    double if_hz;             /* signal.IF            (initParameters.m:41) */
+    double code_hz;           /* signal.codeFreqBasis (initParameters.m:44) */
+    int32_t samples_per_ms;   /* signal.Sample = ceil(Fs*1e-3) (initParameters.m:46) */
+    int32_t data_type;        /* file.dataType: 1 real, 2 I/Q   (initParameters.m:37) */
+    int32_t data_precision;   /* file.dataPrecision: 1 int8, 2 int16 (initParameters.m:38) */
+    double freq_min_hz;       /* acq.freqMin  (initParameters.m:52) */
+    double freq_step_hz;      /* acq.freqStep (initParameters.m:51) */
+    int32_t freq_num;         /* acq.freqNum  (initParameters.m:53) */
+    int32_t noncoh_blocks;    /* acq.datalen  (initParameters.m:54): K non-coherent blocks */
+    int32_t coh_ms;           /* M, coherent ms per block; 1 in the reference */
+    int32_t n_prn;            /* number of PRNs searched by THIS handle (a rank's shard) */
+    int32_t prn[GNSSACQ_MAX_PRN]; /* reference: 1..32 (acquisition.m:47) */
+    double snr_threshold_db;  /* 12 (acquisition.m:70) */
+    int32_t device;           /* CUDA device ordinal; -1 = current device */
+    int32_t cluster_ctas;     /* engine variant: CTAs per transform (0 = auto) */
+    int32_t threads;          /* engine variant: threads per CTA (0 = auto) */
+    int32_t keep_surface;     /* debug: also keep the freq_num x samples_per_ms power surface of
+                                 every PRN in HBM for gnssacq_read_surface (costs HBM + bandwidth) */
+} gnssacq_config;
+
+/* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */
+typedef struct gnssacq_result {
+    int32_t prn;
+    int32_t acquired;         /* SNR >= threshold (acquisition.m:70) */
+    int32_t code_phase;       /* codePhase-1, what Acquired.codedelay stores (acquisition.m:74) */
+    int32_t doppler_bin;      /* fbin-1 */
+    double doppler_hz;        /* acquisition.m:64 */
+    double peak;              /* acquisition.m:63 */
+    double noise_meansq;      /* denominator of acquisition.m:67-68 */
+    double snr_db;            /* acquisition.m:67 */
+    double fine_freq_hz;      /* NaN: the fine-frequency stage (acquisition.m:83-127) is not on this path */
+} gnssacq_result;
+
+/* Device-side timings of the last search (CUDA events on the handle's stream), milliseconds. */
+typedef struct gnssacq_stats {
+    float h2d_ms;             /* pinned host -> HBM copy of the IF block (0 for search_device) */
+    float wipeoff_fft_ms;     /* K1: wipe-off (+fold) + forward FFT of every (base, block) */
+    float search_ms;          /* K2: spectrum multiply + inverse transform + |.|^2 accumulate + row peak */
+    float finalize_ms;        /* K4: per-PRN winner, noise floor, SNR, threshold */
+    float d2h_ms;             /* result rows HBM -> host */
+    float total_ms;           /* first event to last event */
+    int32_t kernel_launches;  /* kernels launched by this search */
+    int32_t n_bases;          /* distinct forward transforms per block after the bin-shift identity */
+    int32_t cluster_ctas;     /* engine variant actually used */
+    int32_t threads;
+} gnssacq_stats;
+
+typedef struct gnssacq_handle gnssacq_handle;
+
+const char* gnssacq_version(void);
+
+/* Fill *cfg with initParameters.m's defaults (Opensky front end, 32 PRNs, 41 bins, 20 ms). */
+int gnssacq_config_default(gnssacq_config* cfg);
+
+/* Bytes of IF data one search consumes: samples_per_ms*data_type*data_precision*noncoh_blocks*coh_ms
+ * (the fread count of acquisition.m:29/34 times the sample size). */
+size_t gnssacq_if_bytes(const gnssacq_config* cfg);
+
+/* Build a handle: validates cfg, selects the device, allocates HBM/pinned buffers and fills the
+ * HBM-resident cache of conj(fft(code))/N for cfg->prn[] (replaces acquisition.m:49-51,58). */
+int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out);
+int gnssacq_destroy(gnssacq_handle* h);
+
+/* Last error text of a handle; with h == NULL, of the last failed gnssacq_create on this thread. */
+const char* gnssacq_last_error(const gnssacq_handle* h);
+
+/* Run kernels on this CUDA stream (a cudaStream_t passed as void*); NULL = the handle's own stream. */
+int gnssacq_set_stream(gnssacq_handle* h, void* cuda_stream);
+
+/* The search (replaces acquisition.m:27-80 minus file I/O): `if_samples` is the byte block
+ * acquisition.m:29/34 reads (host memory).  Writes cfg.n_prn rows to out[] in cfg.prn[] order. */
+int gnssacq_search(gnssacq_handle* h, const void* if_samples, size_t nbytes,
+                   gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
+
+/* Same, with the IF block already resident in HBM (device pointer). */
+int gnssacq_search_device(gnssacq_handle* h, const void* d_if_samples, size_t nbytes,
+                          gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
+
+/* Enqueue only (no host synchronisation, results stay in HBM): for back-to-back timing loops.
+ * gnssacq_fetch_results() synchronises and copies the rows of the last enqueued search. */
+int gnssacq_enqueue_device(gnssacq_handle* h, const void* d_if_samples, size_t nbytes);
+int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
+
+/* ---- table generators (host side, replace generateCAcode.m and acquisition.m:50-51) ---- */
+int gnssacq_ca_code(int32_t prn, int8_t out_chips[1023]);
+int gnssacq_code_replica(const gnssacq_config* cfg, int32_t prn, int8_t* out_samples /* samples_per_ms */);
+
+/* ---- diagnostics used by the parity tests ---- */
+/* Power surface of PRN index `prn_index` (row-major freq_num x samples_per_ms floats, lag order of
+ * acquisition.m:59) from the last search; needs cfg.keep_surface = 1. */
+int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out);
+/* Forward DFT of samples_per_ms complex floats (interleaved re,im; host pointers) through the engine. */
+int gnssacq_fft_forward(gnssacq_handle* h, const float* in, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNSSACQ_H_ */

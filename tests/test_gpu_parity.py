@@ -1,0 +1,204 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  `-m gpu`: runs on the B200 box.
+
+Bar (BASELINE.json north_star): code-phase index, Doppler bin and acquired flag bit-exact unless the
+oracle's two best cells differ by < 2e-5 relative; peak and SNR within 1e-4 relative (FP32)."""
+import io
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.acquisition_ref import correlation_surface
+from oracle.synth import SatSpec, VirtualFile, synth_if, urban_spec, opensky_spec
+import gnssacq
+from gnssacq import api
+from helpers import structs, small_spec, oracle_rows, assert_rows_match, METRIC_RTOL
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {6000: [(2, 128), (1, 256)], 26000: [(2, 512), (4, 256), (4, 512)], 58000: [(4, 512), (8, 256)]}
+
+
+def cfg_from(file, signal, acq, prns, **kw):
+    return gnssacq.config_from_structs(file, signal, acq, prns=prns, **kw)
+
+
+@pytest.mark.parametrize("n", [6000, 26000, 58000])
+def test_fft_engine_against_numpy(n):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    want = np.fft.fft(x.astype(np.complex128))
+    for r, t in VARIANTS[n]:
+        cfg = gnssacq.make_config(fs_hz=n * 1e3, if_hz=0.0, samples_per_ms=n, prns=[1], freq_num=1,
+                                  noncoh_blocks=1, cluster_ctas=r, threads=t)
+        with api.Searcher(cfg) as s:
+            got = s.fft_forward(x)
+        err = np.abs(got - want).max() / np.abs(want).max()
+        assert err < 2e-6, (n, r, t, err)
+
+
+@pytest.mark.parametrize("fs,if_hz", [(6e6, 1.25e6), (26e6, 0.0), (58e6, 4.58e6)])
+def test_power_surface_cellwise(fs, if_hz):
+    """Every cell of acquisition.m:59's surface, not just the winner."""
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1000.0, freq_step=500.0, freq_num=5)
+    n = int(signal.Sample)
+    prns = [3, 9, 22]
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 2)
+    file.fid = io.BytesIO(raw_b)
+    raw = oracle.read_if_block(file, signal, 2)
+    for r, t in VARIANTS[n]:
+        cfg = cfg_from(file, signal, acq, prns, keep_surface=True, cluster_ctas=r, threads=t)
+        with api.Searcher(cfg) as s:
+            rows = s.search(raw_b)
+            for i, prn in enumerate(prns):
+                want = correlation_surface(raw, signal, acq, prn)
+                got = s.read_surface(i)
+                assert np.abs(got - want).max() <= 1e-5 * want.max(), (n, r, t, prn)
+                assert int(np.argmax(got)) == int(np.argmax(want))
+        assert_rows_match(rows, oracle_rows(raw_b, file, signal, acq, prns), what=f"N={n} R={r} T={t}")
+
+
+def test_urban_shaped_32prn_default_grid():
+    """BASELINE config 2 shape (26 MHz, IF 0, 41 bins, 32 PRNs), K = 4 to keep the oracle in seconds."""
+    file, signal, acq = structs(26e6, 0.0, datalen=4)
+    raw_b = synth_if(urban_spec(), 0, 4)
+    prns = list(range(1, 33))
+    ref = oracle_rows(raw_b, file, signal, acq, prns)
+    for r, t in VARIANTS[26000]:
+        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t)) as s:
+            rows = s.search(raw_b)
+        ties = assert_rows_match(rows, ref, what=f"urban R={r} T={t}")
+        assert ties <= 2
+    got = {r.prn for r in rows if r.acquired}
+    assert {1, 3, 11} <= got
+
+
+def test_opensky_shaped_32prn_default_grid():
+    """BASELINE config 1 shape (58 MHz, IF 4.58 MHz, 41 bins, 32 PRNs), K = 2."""
+    file, signal, acq = structs(58e6, 4.58e6, datalen=2)
+    raw_b = synth_if(opensky_spec(), 0, 2)
+    prns = list(range(1, 33))
+    ref = oracle_rows(raw_b, file, signal, acq, prns)
+    for r, t in VARIANTS[58000]:
+        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t)) as s:
+            rows = s.search(raw_b)
+        assert_rows_match(rows, ref, what=f"opensky R={r} T={t}")
+
+
+def test_full_k20_urban_truth_recovery_and_wrapper():
+    """Full-size config 2 through the MATLAB-mirroring wrapper: size-independent property = truth table."""
+    spec = urban_spec()
+    file, signal, acq = gnssacq.initParameters(shape="urban")
+    file.fid = VirtualFile(spec)
+    file.skip = 40
+    out, rows = gnssacq.acquisition(file, signal, acq, verbose=False, return_rows=True)
+    assert set(out) == {"sv", "SNR", "Doppler", "codedelay", "fineFreq"}
+    for k in out:
+        assert out[k].dtype == np.float64 and out[k].ndim == 1
+    got = {int(p): (int(c), float(d)) for p, c, d in zip(out["sv"], out["codedelay"], out["Doppler"])}
+    for s in spec.sats:
+        assert s.prn in got, s.prn
+        assert got[s.prn][0] == s.codedelay
+        assert abs(got[s.prn][1] - s.doppler_hz) <= 250.0
+    assert list(out["sv"]) == sorted(out["sv"]) and len(rows) == 32
+    # same block via the raw API: bytes in, identical rows out (idempotence)
+    file.fid.seek(40 * 26000 * 2)
+    raw = file.fid.read(26000 * 2 * 20)
+    rows2 = gnssacq.get_searcher(gnssacq.config_from_structs(file, signal, acq)).search(raw)
+    assert [(r.code_phase, r.doppler_bin, r.peak) for r in rows] == [(r.code_phase, r.doppler_bin, r.peak) for r in rows2]
+    gnssacq.release_all()
+
+
+@pytest.mark.parametrize("data_type,precision", [(1, 1), (2, 2)])
+def test_real_and_int16_formats(data_type, precision):
+    """acquisition.m:28-38: int8 real stays real; int16 is I/Q with per-component mean removed."""
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, data_type=data_type, data_precision=precision, datalen=3)
+    n = int(signal.Sample)
+    spec = small_spec(fs, if_hz, n, data_type=data_type, data_precision=precision,
+                      sigma=16.0 if precision == 1 else 900.0,
+                      sats=[SatSpec(3, 990.0, 1683, 1.2 if precision == 1 else 70.0), SatSpec(22, 1565.0, 17, 1.5 if precision == 1 else 90.0)])
+    raw_b = synth_if(spec, 0, 3)
+    if precision == 2:   # add a DC offset the mean removal must take out
+        a = np.frombuffer(raw_b, "<i2").copy()
+        a[0::2] += 300
+        a[1::2] -= 450
+        raw_b = a.tobytes()
+    prns = [1, 3, 22, 30]
+    ref = oracle_rows(raw_b, file, signal, acq, prns)
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        rows = s.search(raw_b)
+    assert_rows_match(rows, ref, what=f"type={data_type} prec={precision}")
+
+
+@pytest.mark.parametrize("coh_ms,step,num", [(2, 250.0, 9), (5, 100.0, 21)])
+def test_coherent_fold_and_fine_grid(coh_ms, step, num):
+    """SURVEY A.8 extension (BASELINE configs 3 and 5): M-ms coherent fold, sub-kHz Doppler step."""
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1000.0, freq_step=step, freq_num=num)
+    n = int(signal.Sample)
+    spec = small_spec(fs, if_hz, n, sats=[SatSpec(3, 240.0, 1683, 0.5), SatSpec(22, -610.0, 17, 0.6)])
+    raw_b = synth_if(spec, 0, 2 * coh_ms)
+    prns = [3, 8, 22]
+    ref = oracle_rows(raw_b, file, signal, acq, prns, coh_ms=coh_ms)
+    with api.Searcher(cfg_from(file, signal, acq, prns, coh_ms=coh_ms)) as s:
+        rows = s.search(raw_b)
+        assert s.last_stats.n_bases == min(num, int(round(1000.0 / step)))
+    assert_rows_match(rows, ref, what=f"M={coh_ms}")
+
+
+def test_edge_cases():
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    n = int(signal.Sample)
+    prns = [1, 2]
+    cfg = cfg_from(file, signal, acq, prns)
+    with api.Searcher(cfg) as s:
+        # all-zero input: 0/0 -> NaN SNR, nothing acquired, indices = first cell (acquisition.m:62-70)
+        rows = s.search(bytes(s.if_bytes))
+        for r in rows:
+            assert not r.acquired and math.isnan(r.snr_db) and (r.code_phase, r.doppler_bin, r.peak) == (0, 0, 0.0)
+        # short buffer -> error code, no crash
+        with pytest.raises(gnssacq.GnssAcqError) as e:
+            s.search(bytes(s.if_bytes - 2))
+        assert e.value.code == -3
+        # longer buffer than needed is fine (only the first datalen ms are used)
+        raw_b = synth_if(small_spec(fs, if_hz, n), 0, 3)
+        a = s.search(raw_b)
+        b = s.search(raw_b[: s.if_bytes])
+        assert [(r.code_phase, r.peak) for r in a] == [(r.code_phase, r.peak) for r in b]
+    # peak in the first / last lags: the +-(w-1) exclusion window is clipped, not wrapped (acquisition.m:67)
+    for cd in (0, 2, n - 1):
+        spec = small_spec(fs, if_hz, n, sats=[SatSpec(5, 0.0, cd, 3.0)])
+        raw_b = synth_if(spec, 0, 2)
+        ref = oracle_rows(raw_b, file, signal, acq, [5])
+        with api.Searcher(cfg_from(file, signal, acq, [5])) as s:
+            rows = s.search(raw_b)
+        assert rows[0].code_phase == cd
+        assert_rows_match(rows, ref, what=f"edge lag {cd}")
+    # single Doppler bin: the reference's max(max(.)) quirk is NOT replicated
+    file1, signal1, acq1 = structs(fs, if_hz, datalen=2, freq_min=0.0, freq_num=1)
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 2)
+    ref = oracle_rows(raw_b, file1, signal1, acq1, [3], matlab_quirks=False)
+    with api.Searcher(cfg_from(file1, signal1, acq1, [3])) as s:
+        rows = s.search(raw_b)
+    assert_rows_match(rows, ref, what="single bin")
+
+
+def test_prn_shards_concatenate_to_the_full_table():
+    """Multi-GPU sharding is PRN-major: the union of shard tables is byte-identical to the 1-GPU table."""
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    raw_b = synth_if(small_spec(fs, if_hz, int(signal.Sample)), 0, 2)
+    prns = list(range(1, 33))
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        full = [bytes(r) for r in s.search(raw_b)]
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            shard = prns[rank * 32 // world:(rank + 1) * 32 // world]
+            with api.Searcher(cfg_from(file, signal, acq, shard)) as s:
+                parts += [bytes(r) for r in s.search(raw_b)]
+        assert parts == full
