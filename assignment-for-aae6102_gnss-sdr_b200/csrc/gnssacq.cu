@@ -395,7 +395,7 @@ int gnssacq_set_stream(gnssacq_handle* h, void* s) {
     return GNSSACQ_OK;
 }
 
-static int enqueue(gnssacq_handle* h, const void* d_if) {
+static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = nullptr) {
     cudaStream_t s = h->stream;
     h->launches = 0;
     CU(cudaEventRecord(h->ev[1], s));
@@ -436,7 +436,8 @@ static int enqueue(gnssacq_handle* h, const void* d_if) {
     h->launches += 1;
     CU(cudaEventRecord(h->ev[3], s));
     finalize_kernel<<<(h->P + 63) / 64, 64, 0, s>>>(h->d_cand, h->P, h->B, h->N, h->w, h->cfg.freq_min_hz,
-                                                    h->cfg.freq_step_hz, h->cfg.snr_threshold_db, h->d_prn, h->d_res);
+                                                    h->cfg.freq_step_hz, h->cfg.snr_threshold_db, h->d_prn,
+                                                    d_out ? d_out : h->d_res);
     CU(cudaGetLastError());
     h->launches += 1;
     CU(cudaEventRecord(h->ev[4], s));
@@ -450,6 +451,15 @@ int gnssacq_enqueue_device(gnssacq_handle* h, const void* d_if, size_t nbytes) {
     h->have_h2d = false;
     CU(cudaEventRecord(h->ev[0], h->stream));
     return enqueue(h, d_if);
+}
+
+int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if, size_t nbytes, void* d_out_rows) {
+    if (!h || !d_if || !d_out_rows) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (nbytes < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "IF block shorter than noncoh_blocks*coh_ms ms");
+    CU(cudaSetDevice(h->device));
+    h->have_h2d = false;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    return enqueue(h, d_if, (gnssacq_result*)d_out_rows);
 }
 
 int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* st) {

@@ -71,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = (
     "gnssacq_version", "gnssacq_config_default", "gnssacq_if_bytes", "gnssacq_create",
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
-    "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_fetch_results",
+    "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward",
 )
 
@@ -95,6 +95,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_search.argtypes = [vp, vp, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_search_device.argtypes = [vp, vp, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_enqueue_device.argtypes = [vp, vp, C.c_size_t]
+    lib.gnssacq_enqueue_device_out.argtypes = [vp, vp, C.c_size_t, vp]
     lib.gnssacq_fetch_results.argtypes = [vp, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_ca_code.argtypes = [C.c_int32, vp]
     lib.gnssacq_code_replica.argtypes = [C.POINTER(Config), C.c_int32, vp]
@@ -211,6 +212,10 @@ class Searcher:
 
     def enqueue_device(self, dev_ptr: int, nbytes: int) -> None:
         self._check(lib.gnssacq_enqueue_device(self._h, C.c_void_p(dev_ptr), nbytes))
+
+    def enqueue_device_out(self, dev_ptr: int, nbytes: int, out_dev_ptr: int) -> None:
+        """Stream-ordered search whose result rows land in caller-owned HBM (e.g. an NCCL send buffer)."""
+        self._check(lib.gnssacq_enqueue_device_out(self._h, C.c_void_p(dev_ptr), nbytes, C.c_void_p(out_dev_ptr)))
 
     def fetch(self) -> List[Result]:
         out = (Result * self.cfg.n_prn)()

@@ -124,6 +124,10 @@ int gnssacq_search_device(gnssacq_handle* h, const void* d_if_samples, size_t nb
  * gnssacq_fetch_results() synchronises and copies the rows of the last enqueued search. */
 int gnssacq_enqueue_device(gnssacq_handle* h, const void* d_if_samples, size_t nbytes);
 int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
+/* Enqueue only, and have K4 write the cfg.n_prn result rows straight into caller-owned HBM
+ * (`d_out_rows`, n_prn * sizeof(gnssacq_result) bytes) -- e.g. the send buffer of the NCCL
+ * all-gather that assembles the per-rank PRN shards.  Stream-ordered; no host synchronisation. */
+int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if_samples, size_t nbytes, void* d_out_rows);
 
 /* ---- table generators (host side, replace generateCAcode.m and acquisition.m:50-51) ---- */
 int gnssacq_ca_code(int32_t prn, int8_t out_chips[1023]);
