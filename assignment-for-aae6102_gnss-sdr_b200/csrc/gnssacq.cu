@@ -5,6 +5,7 @@
 // plan, kernel sequencing on one stream, and K4 (per-PRN winner, noise floor, SNR,
 // threshold: acquisition.m:62-70).  No CPU fallback: every numeric step of the search runs in the
 // sm_100a kernels of gnss_kernels.cuh.
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -118,6 +119,24 @@ __global__ void sum_int16_kernel(const int16_t* __restrict__ s, long long n_pair
 __global__ void means_kernel(const long long* __restrict__ sums, long long n_pairs, double* __restrict__ means) {
     means[0] = (double)sums[0] / (double)n_pairs;
     means[1] = (double)sums[1] / (double)n_pairs;
+}
+
+// FP32 FMA peak probe: 16 independent FFMA chains per thread, 8 CTAs x 256 threads per SM.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
 }
 
 }  // namespace
@@ -511,6 +530,39 @@ int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out) {
     CU(cudaStreamSynchronize(h->stream));
     const size_t n = (size_t)h->B * h->N;
     CU(cudaMemcpy(out, h->d_surface + (size_t)prn_index * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_fp32_peak_tflops(int32_t device, double* out_tflops) {
+    gnssacq_handle* h = nullptr;
+    if (!out_tflops) return GNSSACQ_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, GNSSACQ_ERR_NO_DEVICE, "no CUDA device"); }
+    if (device < 0) cudaGetDevice(&device);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    float* d = nullptr;
+    CU(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        fma_peak_kernel<<<blocks, 256>>>(d, iters, 1.0000001f, 1e-7f);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *out_tflops = best;
     return GNSSACQ_OK;
 }
 

@@ -72,7 +72,7 @@ EXPORTS = (
     "gnssacq_version", "gnssacq_config_default", "gnssacq_if_bytes", "gnssacq_create",
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
-    "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward",
+    "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops",
 )
 
 
@@ -101,6 +101,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_code_replica.argtypes = [C.POINTER(Config), C.c_int32, vp]
     lib.gnssacq_read_surface.argtypes = [vp, C.c_int32, vp]
     lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
+    lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
 
@@ -155,6 +156,15 @@ def code_replica(cfg: Config, prn: int) -> np.ndarray:
     if rc:
         raise GnssAcqError(rc, STATUS.get(rc, "?"))
     return out
+
+
+def fp32_peak_tflops(device: int = -1) -> float:
+    """Measured FP32 FMA throughput of the device (TFLOP/s), the FP32 roofline denominator."""
+    out = C.c_double()
+    rc = lib.gnssacq_fp32_peak_tflops(device, C.byref(out))
+    if rc:
+        raise GnssAcqError(rc, (lib.gnssacq_last_error(None) or b"").decode())
+    return out.value
 
 
 class Searcher:

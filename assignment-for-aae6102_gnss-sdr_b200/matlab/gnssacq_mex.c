@@ -1,0 +1,101 @@
+/* gnssacq_mex.c -- MEX gateway from MATLAB to libgnssacq.so (include/gnssacq.h).
+ *
+ *   rows = gnssacq_mex(raw_int8_or_int16, cfg)
+ *
+ * `raw` is the block acquisition.m:29/34 reads, passed as int8 (or int16) WITHOUT conversion to
+ * double; `cfg` is a scalar struct whose fields are named after gnssacq_config.  Returns an
+ * n_prn x 8 double matrix, one row per searched PRN:
+ *   [prn acquired code_phase doppler_bin doppler_hz peak noise_meansq snr_db]
+ * One handle is kept in a static between calls (mexLock) and rebuilt only when cfg changes; it is
+ * destroyed by mexAtExit.  Library errors become MATLAB errors gnssacq:<code>.
+ *
+ * SOURCE-ONLY DELIVERABLE: neither MATLAB nor Octave (mex.h) exists in the build image, so this
+ * file is compile-checked against tests/stubs/mex.h only.  Build on a MATLAB host with
+ *   mex -I<repo>/include gnssacq_mex.c -L<repo>/assignment-for-aae6102_gnss-sdr_b200/gnssacq -lgnssacq
+ */
+#include <string.h>
+#include "mex.h"
+#include "gnssacq.h"
+
+static gnssacq_handle* g_handle = NULL;
+static gnssacq_config g_cfg;
+static int g_have_cfg = 0;
+
+static void at_exit(void) {
+    if (g_handle) { gnssacq_destroy(g_handle); g_handle = NULL; }
+}
+
+static double field(const mxArray* s, const char* name, double dflt) {
+    const mxArray* f = mxGetField(s, 0, name);
+    return (f && mxGetNumberOfElements(f) >= 1) ? mxGetScalar(f) : dflt;
+}
+
+static void fail(int rc, const char* msg) {
+    char id[32];
+    sprintf(id, "gnssacq:e%d", -rc);
+    mexErrMsgIdAndTxt(id, "%s", msg ? msg : "gnssacq error");
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    gnssacq_config c;
+    const mxArray* prn;
+    gnssacq_result* rows;
+    size_t nbytes;
+    double* out;
+    int rc, i;
+
+    if (nrhs != 2 || !mxIsStruct(prhs[1])) fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg)");
+    if (!(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
+
+    gnssacq_config_default(&c);
+    c.fs_hz = field(prhs[1], "fs_hz", c.fs_hz);
+    c.if_hz = field(prhs[1], "if_hz", c.if_hz);
+    c.code_hz = field(prhs[1], "code_hz", c.code_hz);
+    c.samples_per_ms = (int32_t)field(prhs[1], "samples_per_ms", c.samples_per_ms);
+    c.data_type = (int32_t)field(prhs[1], "data_type", c.data_type);
+    c.data_precision = (int32_t)field(prhs[1], "data_precision", c.data_precision);
+    c.freq_min_hz = field(prhs[1], "freq_min_hz", c.freq_min_hz);
+    c.freq_step_hz = field(prhs[1], "freq_step_hz", c.freq_step_hz);
+    c.freq_num = (int32_t)field(prhs[1], "freq_num", c.freq_num);
+    c.noncoh_blocks = (int32_t)field(prhs[1], "noncoh_blocks", c.noncoh_blocks);
+    c.coh_ms = (int32_t)field(prhs[1], "coh_ms", c.coh_ms);
+    c.snr_threshold_db = field(prhs[1], "snr_threshold_db", c.snr_threshold_db);
+    c.device = (int32_t)field(prhs[1], "device", -1);
+    prn = mxGetField(prhs[1], 0, "prn");
+    if (prn) {
+        size_t n = mxGetNumberOfElements(prn);
+        const double* p = mxGetPr(prn);
+        if (n > GNSSACQ_MAX_PRN) fail(GNSSACQ_ERR_INVALID_ARG, "too many PRNs");
+        c.n_prn = (int32_t)n;
+        for (i = 0; i < GNSSACQ_MAX_PRN; ++i) c.prn[i] = (i < (int)n) ? (int32_t)p[i] : 0;
+    }
+
+    if (!g_handle || !g_have_cfg || memcmp(&c, &g_cfg, sizeof c) != 0) {
+        if (g_handle) { gnssacq_destroy(g_handle); g_handle = NULL; }
+        rc = gnssacq_create(&c, &g_handle);
+        if (rc != GNSSACQ_OK) fail(rc, gnssacq_last_error(NULL));
+        if (!g_have_cfg) { mexLock(); mexAtExit(at_exit); }
+        g_cfg = c;
+        g_have_cfg = 1;
+    }
+
+    nbytes = mxGetNumberOfElements(prhs[0]) * mxGetElementSize(prhs[0]);
+    rows = (gnssacq_result*)mxMalloc(sizeof(gnssacq_result) * (size_t)c.n_prn);
+    rc = gnssacq_search(g_handle, mxGetData(prhs[0]), nbytes, rows, NULL);
+    if (rc != GNSSACQ_OK) { mxFree(rows); fail(rc, gnssacq_last_error(g_handle)); }
+
+    plhs[0] = mxCreateDoubleMatrix((mwSize)c.n_prn, 8, mxREAL);
+    out = mxGetPr(plhs[0]);
+    for (i = 0; i < c.n_prn; ++i) {
+        out[i + 0 * c.n_prn] = rows[i].prn;
+        out[i + 1 * c.n_prn] = rows[i].acquired;
+        out[i + 2 * c.n_prn] = rows[i].code_phase;
+        out[i + 3 * c.n_prn] = rows[i].doppler_bin;
+        out[i + 4 * c.n_prn] = rows[i].doppler_hz;
+        out[i + 5 * c.n_prn] = rows[i].peak;
+        out[i + 6 * c.n_prn] = rows[i].noise_meansq;
+        out[i + 7 * c.n_prn] = rows[i].snr_db;
+    }
+    mxFree(rows);
+    (void)nlhs;
+}

@@ -137,6 +137,10 @@ int gnssacq_code_replica(const gnssacq_config* cfg, int32_t prn, int8_t* out_sam
 /* Power surface of PRN index `prn_index` (row-major freq_num x samples_per_ms floats, lag order of
  * acquisition.m:59) from the last search; needs cfg.keep_surface = 1. */
 int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out);
+/* Measured FP32 FMA throughput of `device` in TFLOP/s (2 flops per FFMA; dependent-chain-free FFMA
+ * loop on every SM, CUDA-event timed): the denominator of the FP32 roofline, since
+ * MEASURED_PEAKS.json only records HBM and BF16 tensor peaks. */
+int gnssacq_fp32_peak_tflops(int32_t device, double* out_tflops);
 /* Forward DFT of samples_per_ms complex floats (interleaved re,im; host pointers) through the engine. */
 int gnssacq_fft_forward(gnssacq_handle* h, const float* in, float* out);
 

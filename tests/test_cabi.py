@@ -102,3 +102,12 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(gnssacq.GnssAcqError) as e:
         gnssacq.Searcher(gnssacq.default_config())
     assert e.value.code == -5
+
+
+def test_mex_gateway_compiles_against_header():
+    """matlab/gnssacq_mex.c is source-only here (no MATLAB): syntax/type-check it against the real
+    gnssacq.h and a stub mex.h so it cannot drift from the ABI."""
+    import subprocess
+    src = os.path.join(ROOT, "assignment-for-aae6102_gnss-sdr_b200", "matlab", "gnssacq_mex.c")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tests", "stubs"), src])
