@@ -13,8 +13,8 @@
 //   pass1  load (functor) + DFT-Q over c          task = (a_local, b)
 //   pass2  125 = 5 x 25 : DFT-5 over b1 + W125    task = (row, b2),  b = 25 b1 + b2
 //   pass3  DFT-25 over b2                         task = (row, k1);  pos 25 k1 + k2 holds b' = k1 + 5 k2
-//   pass4  DFT-16 over a, columns split over the R CTAs; reads the other CTAs'
-//          D buffers through distributed shared memory; store functor
+//   pass4  DFT-16 over a, columns split over the R CTAs (two adjacent columns per task, 16-byte
+//          loads); reads the other CTAs' D buffers through distributed shared memory; store functor
 //          (|.|^2 accumulate for the search, spectrum store for K0/K1)
 // The functions below do ONE task each and take the thread's task index, so the
 // same code runs under the CUDA kernels (gnss_kernels.cu) and under the CPU
@@ -36,6 +36,7 @@ template <int Q>
 struct Geo {
     static constexpr int N = 2000 * Q;
     static constexpr int ROW = 125 * Q;           // columns (c', pos) per a-row
+    static constexpr int NX = 16 * (2 * Q - 1) * 125;   // elements of a c-extended forward spectrum (K1 output)
     static constexpr int M1 = 125 * Q, M2 = 16 * Q, M3 = 2000;
     static constexpr int INV1 = cmodinv(M1 % 16, 16);
     static constexpr int INV2 = cmodinv(M2 % 125, 125);
@@ -73,38 +74,61 @@ template <int Q, int R>
 struct Split {
     static_assert(R == 1 || R == 2 || R == 4 || R == 8, "cluster size");
     static constexpr int A = 16 / R;                       // a-rows per CTA
-    static constexpr int ROW = Geo<Q>::ROW;
-    static constexpr int CH = (ROW + R - 1) / R;           // pass-4 columns per CTA
-    static constexpr int D_ELEMS = A * ROW;                // cf per CTA
+    static constexpr int ROW = Geo<Q>::ROW;                // real columns per a-row
+    static constexpr int RS = ROW + (ROW & 1);             // a-row stride in cf: even, so column pairs are 16-B aligned
+    static constexpr int CH = 2 * ((ROW + 2 * R - 1) / (2 * R));   // pass-4 columns per CTA (even)
+    static constexpr int D_ELEMS = A * RS;                 // cf per CTA
     static constexpr int ACC_ELEMS = 16 * CH;              // floats per CTA
+    static constexpr int NR = A * Q;                       // (a_local, c') rows of 125 per CTA
     static constexpr int P1_TASKS = A * 125;
-    static constexpr int P2_TASKS = A * Q * 25;
-    static constexpr int P3_TASKS = A * Q * 5;
-    static constexpr int P4_TASKS = CH;
+    static constexpr int P2_TASKS = NR * 25;
+    static constexpr int P3_TASKS = NR * 5;
+    static constexpr int P4_TASKS = CH / 2;                // column PAIRS
 };
 
 // ------------------------------------------------------------------ pass 1
+// compute half: load (functor) + DFT-Q over c, result left in registers
 template <int Q, int R, class Loader>
-GNSS_HD void pass1_task(int task, int rank, const Loader& ld, cf* __restrict__ D) {
+GNSS_HD void pass1_compute(int task, int rank, const Loader& ld, cf (&z)[Q]) {
     using S = Split<Q, R>;
     const int al = task / 125, b = task - al * 125;
-    const int a = rank * S::A + al;
-    cf z[Q];
-    ld.template load<Q>(a, b, z);
+    ld.template load<Q>(rank * S::A + al, b, z);
     dft_odd<Q>(z);
-    cf* dst = D + (al * Q) * 125 + b;
+}
+// store half: D[a_local][c'][b]
+template <int Q, int R>
+GNSS_HD void pass1_store(int task, const cf (&z)[Q], cf* __restrict__ D) {
+    using S = Split<Q, R>;
+    const int al = task / 125, b = task - al * 125;
+    cf* dst = D + al * S::RS + b;
     static_for<0, Q>([&](auto cc) {
         constexpr int C = decltype(cc)::value;
         dst[C * 125] = z[C];
     });
 }
+template <int Q, int R, class Loader>
+GNSS_HD void pass1_task(int task, int rank, const Loader& ld, cf* __restrict__ D) {
+    cf z[Q];
+    pass1_compute<Q, R>(task, rank, ld, z);
+    pass1_store<Q, R>(task, z, D);
+}
 
 // ------------------------------------------------------------------ pass 2
-// tw125[j] = exp(-2*pi*i*j/125), j in [0,125)
+// tw125[j] = exp(-2*pi*i*j/125), j in [0,125).  Task -> (b2 = task / NR, row = task % NR): consecutive
+// lanes walk consecutive rows (stride 125 cf = 13 bank-pairs mod 16: conflict-free) and share b2, so the
+// twiddle reads are broadcasts.
+template <int Q, int R>
+GNSS_HD cf* pass2_ptr(int task, cf* __restrict__ D, int& b2) {
+    using S = Split<Q, R>;
+    b2 = task / S::NR;
+    const int row = task - b2 * S::NR;
+    const int al = row / Q;
+    return D + row * 125 + al * (S::RS - S::ROW) + b2;
+}
 template <int Q, int R>
 GNSS_HD void pass2_task(int task, cf* __restrict__ D, const cf* __restrict__ tw125) {
-    const int row = task / 25, b2 = task - row * 25;
-    cf* p = D + row * 125 + b2;
+    int b2;
+    cf* p = pass2_ptr<Q, R>(task, D, b2);
     cf u[5] = {p[0], p[25], p[50], p[75], p[100]};
     dft_odd<5>(u);
     p[0] = u[0];
@@ -113,11 +137,37 @@ GNSS_HD void pass2_task(int task, cf* __restrict__ D, const cf* __restrict__ tw1
         p[25 * K1] = cmul(u[K1], tw125[b2 * K1]);
     });
 }
+// two tasks at once: all loads, then all math, then all stores (memory-level parallelism)
+template <int Q, int R>
+GNSS_HD void pass2_task2(int t0, int t1, cf* __restrict__ D, const cf* __restrict__ tw125) {
+    int b20, b21;
+    cf* p0 = pass2_ptr<Q, R>(t0, D, b20);
+    cf* p1 = pass2_ptr<Q, R>(t1, D, b21);
+    cf u[5] = {p0[0], p0[25], p0[50], p0[75], p0[100]};
+    cf v[5] = {p1[0], p1[25], p1[50], p1[75], p1[100]};
+    cf wu[5], wv[5];
+    static_for<1, 5>([&](auto kc) {
+        constexpr int K1 = decltype(kc)::value;
+        wu[K1] = tw125[b20 * K1];
+        wv[K1] = tw125[b21 * K1];
+    });
+    dft_odd<5>(u);
+    dft_odd<5>(v);
+    p0[0] = u[0];
+    p1[0] = v[0];
+    static_for<1, 5>([&](auto kc) {
+        constexpr int K1 = decltype(kc)::value;
+        p0[25 * K1] = cmul(u[K1], wu[K1]);
+        p1[25 * K1] = cmul(v[K1], wv[K1]);
+    });
+}
 
 // ------------------------------------------------------------------ pass 3
 template <int Q, int R>
 GNSS_HD void pass3_task(int task, cf* __restrict__ D) {
-    cf* p = D + task * 25;            // task = row*5 + k1  ->  offset row*125 + 25*k1
+    using S = Split<Q, R>;
+    const int al = task / (5 * Q);    // task = row*5 + k1, row = a_local*Q + c'
+    cf* p = D + task * 25 + al * (S::RS - S::ROW);   // row*125 + 25*k1 (+ a-row padding)
     cf v[25];
     static_for<0, 25>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
@@ -131,40 +181,47 @@ GNSS_HD void pass3_task(int task, cf* __restrict__ D) {
 }
 
 // ------------------------------------------------------------------ pass 4
-// Dall[r] = D buffer of cluster CTA r (DSMEM-mapped on the GPU).
+// Dall[r] = D buffer of cluster CTA r (DSMEM-mapped on the GPU).  One task = two adjacent columns:
+// the 16 rows are fetched with 16-byte loads (half the number of remote requests).
+struct alignas(16) cf2 {
+    cf lo, hi;
+};
 template <int Q, int R, class Storer>
-GNSS_HD void pass4_task(int t, int rank, cf* const* Dall, Storer& st) {
+GNSS_HD void pass4_task(int j, int rank, cf* const* Dall, Storer& st) {
     using S = Split<Q, R>;
+    const int t = 2 * j;
     const int col = rank * S::CH + t;
     if (t >= S::CH || col >= S::ROW) return;
-    cf w[16];
+    cf w0[16], w1[16];
     static_for<0, 16>([&](auto ac) {
         constexpr int Aidx = decltype(ac)::value;
-        w[Aidx] = Dall[Aidx / S::A][(Aidx % S::A) * S::ROW + col];
+        const cf2 v = *reinterpret_cast<const cf2*>(Dall[Aidx / S::A] + (Aidx % S::A) * S::RS + col);
+        w0[Aidx] = v.lo;
+        w1[Aidx] = v.hi;
     });
-    dft16(w);                          // w[4*k1+k2] = Y[a' = k1 + 4*k2]
-    st.template store<Q, R>(col, t, w);
+    dft16(w0);                         // w[4*k1+k2] = Y[a' = k1 + 4*k2]
+    dft16(w1);
+    st.template store2<Q, R>(col, t, w0, w1);
 }
 
 // ================================================================== functors
 // ---- search (K2): Z = Cc * X_base[k - s], accumulate |Y|^2 ----
 struct SearchLoader {
-    const cf* __restrict__ cc;      // conj(fft(code))/N of this PRN, G layout
-    const cf* __restrict__ x;       // fft(wiped-off block) of this (base, block), G layout
+    const cf* __restrict__ cc;      // conj(fft(code))/N of this PRN, G layout [16][Q][125]
+    const cf* __restrict__ x;       // fft(wiped-off block) of this (base, block), c-extended G layout
+                                    // [16][2Q-1][125] (plane c and c+Q hold the same data), so the
+                                    // rotation (c - sc) mod Q is a plain offset
     int sa, sb, sc;                 // bin shift in Good coordinates
     template <int Q>
     GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
         const int as = (a - sa) & 15;
         int bs = b - sb; if (bs < 0) bs += 125;
+        const int c0 = (sc == 0) ? 0 : Q - sc;       // (0 - sc) mod Q
         const cf* pc = cc + (a * Q) * 125 + b;
-        const cf* px = x + (as * Q) * 125 + bs;
-        int cs = (sc == 0) ? 0 : Q - sc;             // (0 - sc) mod Q
+        const cf* px = x + (as * (2 * Q - 1) + c0) * 125 + bs;
         static_for<0, Q>([&](auto c_) {
             constexpr int C = decltype(c_)::value;
-            const cf cv = ld_ro(pc + C * 125);
-            const cf xv = ld_ro(px + cs * 125);
-            z[C] = cmul(cv, xv);
-            cs = (cs + 1 == Q) ? 0 : cs + 1;
+            z[C] = cmul(ld_ro(pc + C * 125), ld_ro(px + C * 125));
         });
     }
 };
@@ -172,12 +229,16 @@ struct SearchLoader {
 struct PowerAccumStorer {
     float* __restrict__ acc;        // [16][CH] floats of this CTA
     template <int Q, int R>
-    GNSS_HD void store(int /*col*/, int t, const cf (&w)[16]) {
+    GNSS_HD void store2(int /*col*/, int t, const cf (&w0)[16], const cf (&w1)[16]) {
         constexpr int CH = Split<Q, R>::CH;
         static_for<0, 16>([&](auto i_) {
             constexpr int I = decltype(i_)::value;               // w[I], I = 4*k1 + k2
             constexpr int AP = (I / 4) + 4 * (I % 4);            // a' = k1 + 4*k2
-            acc[AP * CH + t] += cnorm(w[I]);
+            cf* p = reinterpret_cast<cf*>(acc + AP * CH + t);    // t even, CH even: 8-byte aligned
+            cf v = *p;
+            v.x += cnorm(w0[I]);
+            v.y += cnorm(w1[I]);
+            *p = v;
         });
     }
 };
@@ -187,12 +248,14 @@ struct SpectrumStorer {
     cf* __restrict__ out;
     float scale;                    // 1 for K1, 1/N for K0
     int conj;                       // 1 for K0 (store conj(fft(code))/N)
+    int extended;                   // 1 for K1: c-extended layout [16][2Q-1][125], planes c and c+Q
     template <int Q, int R>
-    GNSS_HD void store(int col, int /*t*/, const cf (&w)[16]) {
+    GNSS_HD void store1(int col, const cf (&w)[16]) {
         using G = Geo<Q>;
         const int cp = col / 125, pos = col - cp * 125;
         const int bp = G::bprime_of_pos(pos);
         const int bg = (bp * G::INV2) % 125, cg = (cp * G::INV3) % Q;
+        const int planes = extended ? 2 * Q - 1 : Q;
         static_for<0, 16>([&](auto i_) {
             constexpr int I = decltype(i_)::value;
             constexpr int AP = (I / 4) + 4 * (I % 4);
@@ -200,8 +263,14 @@ struct SpectrumStorer {
             cf v = w[I];
             v.x *= scale;
             v.y *= conj ? -scale : scale;
-            out[G::gidx(AG, bg, cg)] = v;
+            out[(AG * planes + cg) * 125 + bg] = v;
+            if (extended && cg + Q < planes) out[(AG * planes + cg + Q) * 125 + bg] = v;
         });
+    }
+    template <int Q, int R>
+    GNSS_HD void store2(int col, int /*t*/, const cf (&w0)[16], const cf (&w1)[16]) {
+        store1<Q, R>(col, w0);
+        if (col + 1 < Geo<Q>::ROW) store1<Q, R>(col + 1, w1);
     }
 };
 

@@ -33,14 +33,40 @@ struct NaturalLoader {
 struct NaturalStorer {
     cf* __restrict__ out;
     template <int Q, int R>
-    __device__ __forceinline__ void store(int col, int, const cf (&w)[16]) {
+    __device__ __forceinline__ void store2(int col, int, const cf (&w0)[16], const cf (&w1)[16]) {
         static_for<0, 16>([&](auto i_) {
             constexpr int I = decltype(i_)::value;
             constexpr int AP = (I / 4) + 4 * (I % 4);
-            out[Geo<Q>::lag_of(AP, col)] = w[I];
+            out[Geo<Q>::lag_of(AP, col)] = w0[I];
+            if (col + 1 < Geo<Q>::ROW) out[Geo<Q>::lag_of(AP, col + 1)] = w1[I];
         });
     }
 };
+
+// cluster barrier halves (barrier.cluster): arrive = "I am done with the others' shared memory",
+// wait = "everybody has arrived".  Splitting them lets pass 1's loads and DFT-Q run in the shadow.
+template <int R>
+__device__ __forceinline__ void cl_arrive() {
+    if constexpr (R > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+template <int R>
+__device__ __forceinline__ void cl_wait() {
+    if constexpr (R > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();
+}
+template <int R>
+__device__ __forceinline__ void cl_sync() {
+    cl_arrive<R>();
+    cl_wait<R>();
+}
+
+template <int Q, int R, int T>
+__device__ __forceinline__ void pass2_all(cf* D, const cf* tw, int tid) {
+    using S = Split<Q, R>;
+    int t = tid;
+    for (; t + T < S::P2_TASKS; t += 2 * T) pass2_task2<Q, R>(t, t + T, D, tw);
+    if (t < S::P2_TASKS) pass2_task<Q, R>(t, D, tw);
+}
 
 struct RedScratch {
     float wv[32];
@@ -106,16 +132,41 @@ __device__ __forceinline__ void block_reduce(float& v, int& m, double& s, RedScr
 // passes 1-4 of one transform; cluster-wide barriers around the DSMEM pass
 template <int Q, int R, int T, class Loader, class Storer>
 __device__ __forceinline__ void unit_device(const Loader& ld, Storer& st, cf* D, cf* const* Dall,
-                                            const cf* tw, cg::cluster_group& cluster, int rank, int tid) {
+                                            const cf* tw, int rank, int tid) {
     using S = Split<Q, R>;
     for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
     __syncthreads();
-    for (int t = tid; t < S::P2_TASKS; t += T) pass2_task<Q, R>(t, D, tw);
+    pass2_all<Q, R, T>(D, tw, tid);
     __syncthreads();
     for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
-    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+    cl_sync<R>();
     for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
-    if constexpr (R > 1) cluster.sync(); else __syncthreads();
+    cl_sync<R>();
+}
+
+// Same, for the K-block loop of the search: the barrier that protects D from being overwritten while
+// other CTAs still read it (end of pass 4) is split -- arrive right after pass 4, wait only when
+// pass 1 of the NEXT unit has its DFT-Q results in registers and wants to store them.
+// Precondition: one cl_arrive() is pending on entry; postcondition: one is pending on exit.
+template <int Q, int R, int T, class Loader, class Storer>
+__device__ __forceinline__ void unit_device_pipelined(const Loader& ld, Storer& st, cf* D, cf* const* Dall,
+                                                      const cf* tw, int rank, int tid) {
+    using S = Split<Q, R>;
+    {
+        cf z[Q];
+        const bool has = tid < S::P1_TASKS;
+        if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+        cl_wait<R>();
+        if (has) pass1_store<Q, R>(tid, z, D);
+    }
+    for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+    __syncthreads();
+    pass2_all<Q, R, T>(D, tw, tid);
+    __syncthreads();
+    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+    cl_sync<R>();
+    for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
+    cl_arrive<R>();
 }
 
 #define GNSS_KERNEL_PROLOGUE                                                     \
@@ -139,8 +190,8 @@ __global__ void __launch_bounds__(T, MINB) code_kernel(CodeArgs a) {
     fill_tw125(tw, tid, T);
     __syncthreads();
     CodeLoader ld{a.scode + (size_t)unit * G::N};
-    SpectrumStorer st{a.cc + (size_t)unit * G::N, 1.0f / (float)G::N, 1};
-    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+    SpectrumStorer st{a.cc + (size_t)unit * G::N, 1.0f / (float)G::N, 1, 0};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
 }
 
 template <int Q, int R, int T, int MINB>
@@ -159,8 +210,8 @@ __global__ void __launch_bounds__(T, MINB) wipe_kernel(WipeArgs a) {
     ld.fs_hz = a.fs_hz;
     ld.mean_i = a.means ? (float)a.means[0] : 0.f;
     ld.mean_q = a.means ? (float)a.means[1] : 0.f;
-    SpectrumStorer st{a.x + (size_t)unit * G::N, 1.0f, 0};
-    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+    SpectrumStorer st{a.x + (size_t)unit * G::NX, 1.0f, 0, 1};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
 }
 
 template <int Q, int R, int T, int MINB>
@@ -171,7 +222,7 @@ __global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
     __syncthreads();
     NaturalLoader ld{a.in + (size_t)unit * G::N};
     NaturalStorer st{a.out + (size_t)unit * G::N};
-    unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
 }
 
 template <int Q, int R, int T, int MINB>
@@ -190,12 +241,14 @@ __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
     int sa, sb, sc;
     G::shift_coords(a.bin_shift[b], sa, sb, sc);
     const cf* ccp = a.cc + (size_t)p * G::N;
-    const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::N;
+    const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::NX;
     PowerAccumStorer st{acc};
+    cl_arrive<R>();
     for (int k = 0; k < a.K; ++k) {
-        SearchLoader ld{ccp, xb + (size_t)k * G::N, sa, sb, sc};
-        unit_device<Q, R, T>(ld, st, D, Dall, tw, cluster, rank, tid);
+        SearchLoader ld{ccp, xb + (size_t)k * G::NX, sa, sb, sc};
+        unit_device_pipelined<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
     }
+    cl_wait<R>();
 
     // ---- K3: row peak (first index on ties), sum of squares, windowed sum of squares ----
     float bv = -1.f;

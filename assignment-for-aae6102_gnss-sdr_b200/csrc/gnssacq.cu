@@ -377,7 +377,7 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     CUC(cudaMalloc(&h->d_if, h->if_bytes));
     CUC(cudaMalloc(&h->d_scode, (size_t)h->P * N));
     CUC(cudaMalloc(&h->d_cc, (size_t)h->P * N * sizeof(cf)));
-    CUC(cudaMalloc(&h->d_x, nb * (size_t)h->K * N * sizeof(cf)));
+    CUC(cudaMalloc(&h->d_x, nb * (size_t)h->K * (N / (N / 2000) * (2 * (N / 2000) - 1)) * sizeof(cf)));   // c-extended: N*(2Q-1)/Q
     CUC(cudaMalloc(&h->d_bin_base, h->B * sizeof(int)));
     CUC(cudaMalloc(&h->d_bin_shift, h->B * sizeof(int)));
     CUC(cudaMalloc(&h->d_prn, h->P * sizeof(int)));
@@ -410,7 +410,7 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
 
 int gnssacq_set_stream(gnssacq_handle* h, void* s) {
     if (!h) return GNSSACQ_ERR_INVALID_ARG;
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = (s == GNSSACQ_OWN_STREAM) ? h->own_stream : (cudaStream_t)s;
     return GNSSACQ_OK;
 }
 

@@ -108,7 +108,10 @@ int gnssacq_destroy(gnssacq_handle* h);
 /* Last error text of a handle; with h == NULL, of the last failed gnssacq_create on this thread. */
 const char* gnssacq_last_error(const gnssacq_handle* h);
 
-/* Run kernels on this CUDA stream (a cudaStream_t passed as void*); NULL = the handle's own stream. */
+/* Run kernels on this CUDA stream (a cudaStream_t passed as void*).  NULL is the CUDA legacy default
+ * stream (what torch.cuda.current_stream().cuda_stream returns by default); GNSSACQ_OWN_STREAM
+ * restores the non-blocking stream the handle created for itself (the initial setting). */
+#define GNSSACQ_OWN_STREAM ((void*)(intptr_t)-1)
 int gnssacq_set_stream(gnssacq_handle* h, void* cuda_stream);
 
 /* The search (replaces acquisition.m:27-80 minus file I/O): `if_samples` is the byte block

@@ -19,8 +19,11 @@ static void run_unit(const Loader& ld, Storer* st /*R storers*/, std::vector<std
     for (int r = 0; r < R; ++r) Dall[r] = D[r].data();
     for (int r = 0; r < R; ++r)
         for (int t = 0; t < S::P1_TASKS; ++t) pass1_task<Q, R>(t, r, ld, Dall[r]);
-    for (int r = 0; r < R; ++r)
-        for (int t = 0; t < S::P2_TASKS; ++t) pass2_task<Q, R>(t, Dall[r], tw.data());
+    for (int r = 0; r < R; ++r) {
+        int t = 0;                                   // exercise the two-task form as the kernels do
+        for (; t + 1 < S::P2_TASKS; t += 2) pass2_task2<Q, R>(t, t + 1, Dall[r], tw.data());
+        if (t < S::P2_TASKS) pass2_task<Q, R>(t, Dall[r], tw.data());
+    }
     for (int r = 0; r < R; ++r)
         for (int t = 0; t < S::P3_TASKS; ++t) pass3_task<Q, R>(t, Dall[r]);
     for (int r = 0; r < R; ++r)
@@ -43,7 +46,7 @@ static int code_spectrum(const int8_t* scode, cf* out) {
     auto tw = make_tw125();
     CodeLoader ld{scode};
     SpectrumStorer st[R];
-    for (int r = 0; r < R; ++r) st[r] = SpectrumStorer{out, 1.0f / Geo<Q>::N, 1};
+    for (int r = 0; r < R; ++r) st[r] = SpectrumStorer{out, 1.0f / Geo<Q>::N, 1, 0};
     run_unit<Q, R>(ld, st, D, tw);
     return 0;
 }
@@ -56,7 +59,7 @@ static int wipe_spectrum(const void* raw, int data_type, int precision, int coh_
     auto tw = make_tw125();
     WipeoffLoader ld{raw, data_type, precision, coh_ms, f_hz, fs_hz, mi, mq};
     SpectrumStorer st[R];
-    for (int r = 0; r < R; ++r) st[r] = SpectrumStorer{out, 1.0f, 0};
+    for (int r = 0; r < R; ++r) st[r] = SpectrumStorer{out, 1.0f, 0, 1};
     run_unit<Q, R>(ld, st, D, tw);
     return 0;
 }
@@ -71,7 +74,7 @@ static int search_row(const cf* cc, const cf* x_blocks, int K, int shift, float*
     int sa, sb, sc;
     G::shift_coords(shift, sa, sb, sc);
     for (int k = 0; k < K; ++k) {
-        SearchLoader ld{cc, x_blocks + (size_t)k * G::N, sa, sb, sc};
+        SearchLoader ld{cc, x_blocks + (size_t)k * G::NX, sa, sb, sc};
         PowerAccumStorer st[R];
         for (int r = 0; r < R; ++r) st[r] = PowerAccumStorer{acc[r].data()};
         run_unit<Q, R>(ld, st, D, tw);
@@ -92,6 +95,20 @@ static int search_row(const cf* cc, const cf* x_blocks, int K, int shift, float*
     return 0;
 }
 
+template <int Q>
+static void gx_to_natural(const cf* g, cf* nat) {   // c-extended layout [16][2Q-1][125]; also checks the duplicate planes
+    using G = Geo<Q>;
+    for (int a = 0; a < 16; ++a)
+        for (int b = 0; b < 125; ++b)
+            for (int c = 0; c < Q; ++c) {
+                cf v = g[(a * (2 * Q - 1) + c) * 125 + b];
+                if (c + Q < 2 * Q - 1) {
+                    cf w = g[(a * (2 * Q - 1) + c + Q) * 125 + b];
+                    if (w.x != v.x || w.y != v.y) v = mk(1e30f, 1e30f);
+                }
+                nat[G::good(a, b, c)] = v;
+            }
+}
 template <int Q>
 static void g_to_natural(const cf* g, cf* nat) {
     using G = Geo<Q>;
@@ -119,6 +136,12 @@ int emu_wipe_spectrum(int Q, int R, const void* raw, int data_type, int precisio
 int emu_search_row(int Q, int R, const float* cc, const float* x_blocks, int K, int shift,
                    float* acc_by_lag) {
     ALL((search_row<QQ, RR>((const cf*)cc, (const cf*)x_blocks, K, shift, acc_by_lag)))
+    return -2;
+}
+int emu_gx_to_natural(int Q, const float* g, float* nat) {
+    if (Q == 3) { gx_to_natural<3>((const cf*)g, (cf*)nat); return 0; }
+    if (Q == 13) { gx_to_natural<13>((const cf*)g, (cf*)nat); return 0; }
+    if (Q == 29) { gx_to_natural<29>((const cf*)g, (cf*)nat); return 0; }
     return -2;
 }
 int emu_g_to_natural(int Q, const float* g, float* nat) {

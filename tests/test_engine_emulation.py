@@ -51,12 +51,13 @@ def test_engine_passes_against_numpy(emu, Q, R):
     xs = raw[0::2].astype(float) + 1j * raw[1::2].astype(float)
     n1 = np.arange(1, N + 1)
     f0 = if_hz - 1000.0
-    xg = np.zeros((K, 2 * N), np.float32)
+    NX = 16 * (2 * Q - 1) * 125
+    xg = np.zeros((K, 2 * NX), np.float32)
     for k in range(K):
         blk = np.ascontiguousarray(raw[2 * N * k:2 * N * (k + 1)])
         assert emu.emu_wipe_spectrum(Q, R, P(blk), 2, 1, 1, C.c_double(f0), C.c_double(fs),
                                      C.c_float(0), C.c_float(0), P(xg[k])) == 0
-        assert emu.emu_g_to_natural(Q, P(xg[k]), P(nat)) == 0
+        assert emu.emu_gx_to_natural(Q, P(xg[k]), P(nat)) == 0
         xr = np.fft.fft(xs[N * k:N * (k + 1)] * np.exp(2j * np.pi * f0 * n1 / fs))
         assert np.abs(nat.view(np.complex64) - xr).max() <= 2e-6 * np.abs(xr).max()
 
