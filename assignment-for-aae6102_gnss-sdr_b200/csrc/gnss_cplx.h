@@ -35,6 +35,22 @@ GNSS_HD cf ld_ro(const cf* p) {
 #endif
 }
 
+// 16-byte pair of complex values; ld_cg2 = L2-only (cache-global) load, used for data another SM wrote
+struct alignas(16) cf2 {
+    cf lo, hi;
+};
+GNSS_HD cf2 ld_cg2(const cf2* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    cf2 r;
+    r.lo = mk(v.x, v.y);
+    r.hi = mk(v.z, v.w);
+    return r;
+#else
+    return *p;
+#endif
+}
+
 // ---- compile-time loop: f(std::integral_constant<int, I>) for I in [B, E) ----
 template <int B, int E, class F>
 GNSS_HD void static_for(F&& f) {

@@ -183,9 +183,6 @@ GNSS_HD void pass3_task(int task, cf* __restrict__ D) {
 // ------------------------------------------------------------------ pass 4
 // Dall[r] = D buffer of cluster CTA r (DSMEM-mapped on the GPU).  One task = two adjacent columns:
 // the 16 rows are fetched with 16-byte loads (half the number of remote requests).
-struct alignas(16) cf2 {
-    cf lo, hi;
-};
 template <int Q, int R, class Storer>
 GNSS_HD void pass4_task(int j, int rank, cf* const* Dall, Storer& st) {
     using S = Split<Q, R>;
@@ -200,6 +197,26 @@ GNSS_HD void pass4_task(int j, int rank, cf* const* Dall, Storer& st) {
         w1[Aidx] = v.hi;
     });
     dft16(w0);                         // w[4*k1+k2] = Y[a' = k1 + 4*k2]
+    dft16(w1);
+    st.template store2<Q, R>(col, t, w0, w1);
+}
+
+// Same pass, but the 16 rows come from one flat [16][RS] array in global memory (the L2-resident
+// exchange buffer the cluster's CTAs copied their finished rows into), read with L2-only loads.
+template <int Q, int R, class Storer>
+GNSS_HD void pass4_task_flat(int j, int rank, const cf* __restrict__ X, Storer& st) {
+    using S = Split<Q, R>;
+    const int t = 2 * j;
+    const int col = rank * S::CH + t;
+    if (t >= S::CH || col >= S::ROW) return;
+    cf w0[16], w1[16];
+    static_for<0, 16>([&](auto ac) {
+        constexpr int Aidx = decltype(ac)::value;
+        const cf2 v = ld_cg2(reinterpret_cast<const cf2*>(X + Aidx * S::RS + col));
+        w0[Aidx] = v.lo;
+        w1[Aidx] = v.hi;
+    });
+    dft16(w0);
     dft16(w1);
     st.template store2<Q, R>(col, t, w0, w1);
 }

@@ -25,6 +25,7 @@ struct SearchArgs {
     int w;                 // ceil(Fs/fc) (acquisition.m:66)
     Candidate* cand;       // [P][B]
     float* surface;        // optional [P][B][N] (debug), lag order
+    cf* scratch;           // L2-exchange variant: [clusters][2][16][RS] (double-buffered finished rows)
 };
 
 struct WipeArgs {
@@ -55,6 +56,10 @@ struct VariantOps {
     cudaError_t (*launch_wipe)(const WipeArgs&, int units, cudaStream_t);
     cudaError_t (*launch_natural)(const NaturalArgs&, int units, cudaStream_t);
     cudaError_t (*launch_search)(const SearchArgs&, int rows, cudaStream_t);
+    // L2-exchange persistent variant: `clusters` co-resident clusters loop over the rows
+    cudaError_t (*launch_search_l2x)(const SearchArgs&, int clusters, cudaStream_t);
+    int (*max_clusters_l2x)();             // co-resident clusters of search_kernel_l2x on the current device
+    size_t scratch_bytes_per_cluster;
 };
 
 // defined in gnss_q3.cu / gnss_q13.cu / gnss_q29.cu

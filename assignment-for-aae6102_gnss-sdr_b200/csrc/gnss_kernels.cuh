@@ -316,6 +316,141 @@ __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
     if constexpr (R > 1) cluster.sync();   // keep every CTA's shared memory alive until rank 0 has read it
 }
 
+// K2, L2-exchange variant.  Pass 4 needs every CTA's finished rows; pulling them through DSMEM is
+// bandwidth bound (~10 B/clk/SM each way, ncu r01b: 33 % of the kernel).  Here each CTA copies its
+// finished rows (coalesced 16-B stores) into a double-buffered exchange array that stays L2-resident,
+// signals the cluster barrier, runs pass 1 of the NEXT block while the barrier and the stores drain,
+// and only then waits and runs pass 4 from L2.  D is private again, so only CTA-local barriers guard it.
+// Persistent: gridDim.x / R clusters, each looping over rows; the cluster index selects the exchange slot.
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    (void)Dall;
+    float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
+    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    const int ncl = gridDim.x / R, slot = unit;
+    cf* xch = a.scratch + (size_t)slot * 2 * 16 * S::RS;
+    fill_tw125(tw, tid, T);
+    PowerAccumStorer st{acc};
+
+    for (int row = slot; row < a.P * a.B; row += ncl) {
+        const int p = row % a.P, b = row / a.P;
+        for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+        int sa, sb, sc;
+        G::shift_coords(a.bin_shift[b], sa, sb, sc);
+        const cf* ccp = a.cc + (size_t)p * G::N;
+        const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::NX;
+        {
+            SearchLoader ld{ccp, xb, sa, sb, sc};
+            for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+        }
+        __syncthreads();
+        pass2_all<Q, R, T>(D, tw, tid);
+        __syncthreads();
+        for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+        // Software pipeline over the K blocks.  Per iteration: rows of block k leave for L2 (posted
+        // stores), passes 1-2 of block k+1 run while they drain and while the other CTAs catch up,
+        // then pass 4 of block k reads all 16 rows back from L2, then pass 3 of block k+1.
+        for (int k = 0; k < a.K; ++k) {
+            const bool more = k + 1 < a.K;
+            cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
+            __syncthreads();                           // pass 3 of block k complete in D
+            {
+                const float4* src = reinterpret_cast<const float4*>(D);
+                float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
+                for (int i = tid; i < S::D_ELEMS / 2; i += T) dst[i] = src[i];
+            }
+            if (more) {
+                SearchLoader ld{ccp, xb + (size_t)(k + 1) * G::NX, sa, sb, sc};
+                cf z[Q];
+                const bool has = tid < S::P1_TASKS;
+                if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+                __syncthreads();                       // every thread has finished copying D out
+                if (has) pass1_store<Q, R>(tid, z, D);
+                for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+            }
+            cl_arrive<R>();                            // release: my rows of block k are in L2 by now
+            if (more) {
+                __syncthreads();
+                pass2_all<Q, R, T>(D, tw, tid);
+            }
+            cl_wait<R>();                              // acquire: everybody's rows of block k
+            for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
+            if (more) {
+                __syncthreads();
+                for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+            }
+        }
+        __syncthreads();
+
+        // ---- K3 (identical to search_kernel) ----
+        float bv = -1.f;
+        int bm = INT_MAX;
+        double ss = 0.0;
+        for (int e = tid; e < S::ACC_ELEMS; e += T) {
+            const int ap = e / S::CH, t = e - ap * S::CH;
+            const int col = rank * S::CH + t;
+            if (col < S::ROW) {
+                const float v = acc[e];
+                const int m = G::lag_of(ap, col);
+                if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
+                ss += (double)v * (double)v;
+                if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
+            }
+        }
+        block_reduce<T>(bv, bm, ss, rs);
+        if (tid == 0) { rs->peak = bv; rs->lag = bm; rs->sum_all = ss; }
+        if constexpr (R > 1) cluster.sync(); else __syncthreads();
+        if (tid == 0) {
+            float gv = -1.f;
+            int gm = INT_MAX;
+            for (int r = 0; r < R; ++r) {
+                const RedScratch* o = (R > 1) ? cluster.map_shared_rank(rs, r) : rs;
+                const float ov = o->peak;
+                const int om = o->lag;
+                if (peak_better(ov, om, gv, gm)) { gv = ov; gm = om; }
+            }
+            rs->g_peak = gv;
+            rs->g_lag = gm;
+        }
+        __syncthreads();
+        const int gm = rs->g_lag;
+        double wsum = 0.0;
+        for (int i = tid; i < 2 * a.w - 1; i += T) {
+            const int m = gm - (a.w - 1) + i;
+            if (m >= 0 && m < G::N) {
+                int ap, col;
+                G::cell_of_lag(m, ap, col);
+                if (col / S::CH == rank) {
+                    const float v = acc[ap * S::CH + (col - rank * S::CH)];
+                    wsum += (double)v * (double)v;
+                }
+            }
+        }
+        float dv = -1.f;
+        int dm = INT_MAX;
+        block_reduce<T>(dv, dm, wsum, rs);
+        if (tid == 0) rs->sum_win = wsum;
+        if constexpr (R > 1) cluster.sync(); else __syncthreads();
+        if (rank == 0 && tid == 0) {
+            double s_all = 0.0, s_win = 0.0;
+            for (int r = 0; r < R; ++r) {
+                const RedScratch* o = (R > 1) ? cluster.map_shared_rank(rs, r) : rs;
+                s_all += o->sum_all;
+                s_win += o->sum_win;
+            }
+            Candidate c;
+            c.peak = rs->g_peak;
+            c.lag = rs->g_lag;
+            c.sum_all = s_all;
+            c.sum_win = s_win;
+            a.cand[(size_t)p * a.B + b] = c;
+        }
+        if constexpr (R > 1) cluster.sync(); else __syncthreads();   // slots are rewritten by the next row
+    }
+}
+
 // ------------------------------------------------------------------ launch glue
 template <class K, class A>
 static cudaError_t launch_clustered(K kern, const A& args, int units, int R, int T, size_t smem, cudaStream_t s) {
@@ -345,7 +480,28 @@ struct Variant {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(natural_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(search_kernel_l2x<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
+        if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(search_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
+    }
+    static cudaError_t launch_search_l2x(const SearchArgs& a, int clusters, cudaStream_t s) {
+        return launch_clustered(search_kernel_l2x<Q, R, T, MINB>, a, clusters, R, T, Smem<Q, R>::search, s);
+    }
+    static int max_clusters_l2x() {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(R * 1024), 1, 1);
+        cfg.blockDim = dim3((unsigned)T, 1, 1);
+        cfg.dynamicSmemBytes = Smem<Q, R>::search;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)R;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, search_kernel_l2x<Q, R, T, MINB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return n;
     }
     static cudaError_t launch_code(const CodeArgs& a, int units, cudaStream_t s) {
         return launch_clustered(code_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
@@ -361,7 +517,9 @@ struct Variant {
     }
     static constexpr VariantOps ops() {
         return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, R>::transform,
-                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_search};
+                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_search,
+                          &launch_search_l2x, &max_clusters_l2x,
+                          (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf)};
     }
 };
 

@@ -162,6 +162,8 @@ struct gnssacq_handle {
     Candidate* d_cand = nullptr;
     gnssacq_result* d_res = nullptr;
     float* d_surface = nullptr;
+    cf* d_scratch = nullptr;
+    int l2x_clusters = 0;          // > 0: use the L2-exchange persistent search kernel with this many clusters
     long long* d_sums = nullptr;
     double* d_means = nullptr;
     cf *d_fft_in = nullptr, *d_fft_out = nullptr;
@@ -239,6 +241,7 @@ int validate(const gnssacq_config* c, std::string& why) {
     if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
     for (int i = 0; i < c->n_prn; ++i)
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->exchange < 0 || c->exchange > 2) { why = "exchange must be 0 (auto), 1 (DSMEM) or 2 (L2)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
         why = "samples_per_ms must be 2000*Q (built: Q = 3, 13, 29 -> 6000, 26000, 58000)";
         return GNSSACQ_ERR_UNSUPPORTED_N;
@@ -300,7 +303,7 @@ int gnssacq_destroy(gnssacq_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
     cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
-    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     if (h->h_if) cudaFreeHost(h->h_if);
     if (h->h_res) cudaFreeHost(h->h_res);
@@ -386,6 +389,20 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     CUC(cudaMalloc(&h->d_res, h->P * sizeof(gnssacq_result)));
     CUC(cudaMalloc(&h->d_sums, 2 * sizeof(long long)));
     CUC(cudaMalloc(&h->d_means, 2 * sizeof(double)));
+    // auto: the L2 exchange wins where the DSMEM pull is bandwidth bound (N = 58 000, 4-CTA clusters);
+    // for the smaller transforms the two are within noise and DSMEM needs no scratch (profiles/r01).
+    const bool want_l2x = cfg->exchange == 2 || (cfg->exchange == 0 && Q >= 29);
+    if (want_l2x) {
+        int n = ops->max_clusters_l2x();
+        if (n > h->P * h->B) n = h->P * h->B;
+        if (n > 0) {
+            h->l2x_clusters = n;
+            CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
+        } else if (cfg->exchange == 2) {
+            gnssacq_destroy(h);
+            return fail(nullptr, GNSSACQ_ERR_CUDA, "L2-exchange search kernel cannot be made resident on this device");
+        }
+    }
     if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
     CUC(cudaMallocHost(&h->h_if, h->if_bytes));
     CUC(cudaMallocHost(&h->h_res, h->P * sizeof(gnssacq_result)));
@@ -451,7 +468,9 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.w = h->w;
     sa.cand = h->d_cand;
     sa.surface = h->d_surface;
-    CU(h->ops->launch_search(sa, h->P * h->B, s));
+    sa.scratch = h->d_scratch;
+    if (h->l2x_clusters > 0) CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));
+    else CU(h->ops->launch_search(sa, h->P * h->B, s));
     h->launches += 1;
     CU(cudaEventRecord(h->ev[3], s));
     finalize_kernel<<<(h->P + 63) / 64, 64, 0, s>>>(h->d_cand, h->P, h->B, h->N, h->w, h->cfg.freq_min_hz,
@@ -500,6 +519,8 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
         st->n_bases = (int)h->base_freq.size();
         st->cluster_ctas = h->ops->R;
         st->threads = h->ops->T;
+        st->exchange = h->l2x_clusters > 0 ? 2 : 1;
+        st->resident_clusters = h->l2x_clusters;
     }
     return GNSSACQ_OK;
 }

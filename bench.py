@@ -219,7 +219,7 @@ def run_gpu(args, cfg):
         return gnssacq.make_config(fs_hz=cfg["fs"], if_hz=cfg["if_hz"], samples_per_ms=cfg["n"],
                                    freq_min_hz=cfg["fmin"], freq_step_hz=cfg["fstep"], freq_num=cfg["bins"],
                                    noncoh_blocks=cfg["k"], coh_ms=cfg["m"], prns=prns, device=device,
-                                   cluster_ctas=args.cluster_ctas, threads=args.threads)
+                                   cluster_ctas=args.cluster_ctas, threads=args.threads, exchange=args.exchange)
 
     raw = synth_bytes(cfg)
     shard = CudaShard(factory, PRNS, rank, world, local)
@@ -309,7 +309,8 @@ def run_gpu(args, cfg):
             "data": "synthetic",
             "config": {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
                        "coh_ms": cfg["m"], "prns": 32, "cells": cells, "cell_blocks": cells * cfg["k"],
-                       "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1]},
+                       "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2"}.get(st.exchange),
+                                  "resident_clusters": st.resident_clusters},
                        "sharding": f"PRN-major, {n_local} PRNs on rank 0",
                        "l2": "flushed between steps (256 MiB device memset, outside the per-step event pair)",
                        "latency_ms_32prn": e2e_s / args.steps * 1e3},
@@ -344,6 +345,7 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--cluster-ctas", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--exchange", type=int, default=0, help="0 auto, 1 DSMEM, 2 L2-resident exchange buffer")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -18,7 +18,10 @@ from helpers import structs, small_spec, oracle_rows, assert_rows_match, METRIC_
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {6000: [(2, 128), (1, 256)], 26000: [(2, 512), (4, 256), (4, 512)], 58000: [(4, 512), (8, 256)]}
+# (cluster CTAs, threads, exchange: 1 = DSMEM, 2 = L2-resident buffer)
+VARIANTS = {6000: [(2, 128, 1), (1, 256, 1), (2, 128, 2), (1, 256, 2)],
+            26000: [(2, 512, 1), (4, 256, 1), (4, 512, 1), (2, 512, 2), (4, 256, 2), (4, 512, 2)],
+            58000: [(4, 512, 1), (8, 256, 1), (4, 512, 2), (8, 256, 2)]}
 
 
 def cfg_from(file, signal, acq, prns, **kw):
@@ -30,7 +33,7 @@ def test_fft_engine_against_numpy(n):
     rng = np.random.default_rng(n)
     x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
     want = np.fft.fft(x.astype(np.complex128))
-    for r, t in VARIANTS[n]:
+    for r, t, _ in VARIANTS[n][:3]:
         cfg = gnssacq.make_config(fs_hz=n * 1e3, if_hz=0.0, samples_per_ms=n, prns=[1], freq_num=1,
                                   noncoh_blocks=1, cluster_ctas=r, threads=t)
         with api.Searcher(cfg) as s:
@@ -48,16 +51,16 @@ def test_power_surface_cellwise(fs, if_hz):
     raw_b = synth_if(small_spec(fs, if_hz, n), 0, 2)
     file.fid = io.BytesIO(raw_b)
     raw = oracle.read_if_block(file, signal, 2)
-    for r, t in VARIANTS[n]:
-        cfg = cfg_from(file, signal, acq, prns, keep_surface=True, cluster_ctas=r, threads=t)
+    for r, t, x in VARIANTS[n]:
+        cfg = cfg_from(file, signal, acq, prns, keep_surface=True, cluster_ctas=r, threads=t, exchange=x)
         with api.Searcher(cfg) as s:
             rows = s.search(raw_b)
             for i, prn in enumerate(prns):
                 want = correlation_surface(raw, signal, acq, prn)
                 got = s.read_surface(i)
-                assert np.abs(got - want).max() <= 1e-5 * want.max(), (n, r, t, prn)
+                assert np.abs(got - want).max() <= 1e-5 * want.max(), (n, r, t, x, prn)
                 assert int(np.argmax(got)) == int(np.argmax(want))
-        assert_rows_match(rows, oracle_rows(raw_b, file, signal, acq, prns), what=f"N={n} R={r} T={t}")
+        assert_rows_match(rows, oracle_rows(raw_b, file, signal, acq, prns), what=f"N={n} R={r} T={t} X={x}")
 
 
 def test_urban_shaped_32prn_default_grid():
@@ -66,10 +69,11 @@ def test_urban_shaped_32prn_default_grid():
     raw_b = synth_if(urban_spec(), 0, 4)
     prns = list(range(1, 33))
     ref = oracle_rows(raw_b, file, signal, acq, prns)
-    for r, t in VARIANTS[26000]:
-        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t)) as s:
+    for r, t, x in VARIANTS[26000]:
+        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t, exchange=x)) as s:
             rows = s.search(raw_b)
-        ties = assert_rows_match(rows, ref, what=f"urban R={r} T={t}")
+            assert s.last_stats.exchange == x
+        ties = assert_rows_match(rows, ref, what=f"urban R={r} T={t} X={x}")
         assert ties <= 2
     got = {r.prn for r in rows if r.acquired}
     assert {1, 3, 11} <= got
@@ -81,10 +85,10 @@ def test_opensky_shaped_32prn_default_grid():
     raw_b = synth_if(opensky_spec(), 0, 2)
     prns = list(range(1, 33))
     ref = oracle_rows(raw_b, file, signal, acq, prns)
-    for r, t in VARIANTS[58000]:
-        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t)) as s:
+    for r, t, x in VARIANTS[58000]:
+        with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=r, threads=t, exchange=x)) as s:
             rows = s.search(raw_b)
-        assert_rows_match(rows, ref, what=f"opensky R={r} T={t}")
+        assert_rows_match(rows, ref, what=f"opensky R={r} T={t} X={x}")
 
 
 def test_full_k20_urban_truth_recovery_and_wrapper():
