@@ -25,7 +25,9 @@ struct SearchArgs {
     int w;                 // ceil(Fs/fc) (acquisition.m:66)
     Candidate* cand;       // [P][B]
     float* surface;        // optional [P][B][N] (debug), lag order
-    cf* scratch;           // L2-exchange variant: [clusters][2][16][RS] (double-buffered finished rows)
+    cf* scratch;           // L2-exchange variants: [groups][2][16][RS] (double-buffered finished rows)
+    unsigned* group_ctr;   // coop variant: one arrival counter per CTA group (zeroed before the launch)
+    Candidate* row_slots;  // coop variant: [groups][R] per-CTA partial row results
 };
 
 struct WipeArgs {
@@ -60,6 +62,9 @@ struct VariantOps {
     cudaError_t (*launch_search_l2x)(const SearchArgs&, int clusters, cudaStream_t);
     int (*max_clusters_l2x)();             // co-resident clusters of search_kernel_l2x on the current device
     size_t scratch_bytes_per_cluster;
+    // cluster-free cooperative persistent variant: groups of R CTAs, software barriers through L2
+    cudaError_t (*launch_search_coop)(const SearchArgs&, int groups, cudaStream_t);
+    int (*max_groups_coop)();              // co-resident CTA groups on the current device
 };
 
 // defined in gnss_q3.cu / gnss_q13.cu / gnss_q29.cu

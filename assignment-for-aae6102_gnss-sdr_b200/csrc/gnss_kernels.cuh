@@ -451,6 +451,163 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
     }
 }
 
+// K2, cooperative variant: no thread-block clusters at all.  A transform is shared by a GROUP of R
+// consecutive CTAs of a cooperative (all-co-resident) persistent grid; rows are exchanged through the
+// L2-resident buffer exactly as in search_kernel_l2x, and the group barrier is an arrival counter in
+// global memory (one red.release by thread 0 after the CTA barrier, one ld.acquire spin by thread 0
+// before it).  Gains over the cluster kernels: every SM is usable (4-CTA clusters leave 16 of 148 SMs
+// idle, ncu r01: 33 clusters resident), and only one thread pays the release fence.
+__device__ __forceinline__ void group_arrive(unsigned* ctr) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target) {
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
+}
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
+    using S = Split<Q, R>;
+    using G = Geo<Q>;
+    const int tid = threadIdx.x;
+    const int rank = blockIdx.x % R, group = blockIdx.x / R, ngroups = gridDim.x / R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* D = reinterpret_cast<cf*>(smem_raw);
+    float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
+    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    cf* xch = a.scratch + (size_t)group * 2 * 16 * S::RS;
+    unsigned* ctr = a.group_ctr + group;
+    Candidate* slots = a.row_slots + (size_t)group * R;
+    unsigned target = 0;                       // arrivals expected so far (R per barrier)
+    fill_tw125(tw, tid, T);
+    PowerAccumStorer st{acc};
+
+    for (int row = group; row < a.P * a.B; row += ngroups) {
+        const int p = row % a.P, b = row / a.P;
+        for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+        int sa, sb, sc;
+        G::shift_coords(a.bin_shift[b], sa, sb, sc);
+        const cf* ccp = a.cc + (size_t)p * G::N;
+        const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::NX;
+        {
+            SearchLoader ld{ccp, xb, sa, sb, sc};
+            for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+        }
+        __syncthreads();
+        pass2_all<Q, R, T>(D, tw, tid);
+        __syncthreads();
+        for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+        for (int k = 0; k < a.K; ++k) {
+            const bool more = k + 1 < a.K;
+            cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
+            __syncthreads();                           // pass 3 of block k complete in D
+            {
+                const float4* src = reinterpret_cast<const float4*>(D);
+                float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
+                for (int i = tid; i < S::D_ELEMS / 2; i += T) dst[i] = src[i];
+            }
+            target += R;
+            if (more) {
+                SearchLoader ld{ccp, xb + (size_t)(k + 1) * G::NX, sa, sb, sc};
+                cf z[Q];
+                const bool has = tid < S::P1_TASKS;
+                if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+                __syncthreads();                       // every thread has issued its copy stores
+                if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier)
+                if (has) pass1_store<Q, R>(tid, z, D);
+                for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+                __syncthreads();
+                pass2_all<Q, R, T>(D, tw, tid);
+            } else {
+                __syncthreads();
+                if (tid == 0) group_arrive(ctr);
+            }
+            if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of block k are in L2
+            __syncthreads();
+            for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
+            if (more) {
+                // pass 2 of block k+1 finished before the barrier above
+                for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+            }
+        }
+        __syncthreads();
+
+        // ---- K3 through global slots ----
+        float bv = -1.f;
+        int bm = INT_MAX;
+        double ss = 0.0;
+        for (int e = tid; e < S::ACC_ELEMS; e += T) {
+            const int ap = e / S::CH, t = e - ap * S::CH;
+            const int col = rank * S::CH + t;
+            if (col < S::ROW) {
+                const float v = acc[e];
+                const int m = G::lag_of(ap, col);
+                if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
+                ss += (double)v * (double)v;
+                if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
+            }
+        }
+        block_reduce<T>(bv, bm, ss, rs);
+        target += R;
+        if (tid == 0) {
+            Candidate c; c.peak = bv; c.lag = bm; c.sum_all = ss; c.sum_win = 0.0;
+            slots[rank] = c;
+            group_arrive(ctr);
+            group_spin(ctr, target);
+            float gv = -1.f;
+            int gm = INT_MAX;
+            for (int r = 0; r < R; ++r) {
+                const float ov = __ldcg(&slots[r].peak);
+                const int om = __ldcg(&slots[r].lag);
+                if (peak_better(ov, om, gv, gm)) { gv = ov; gm = om; }
+            }
+            rs->g_peak = gv;
+            rs->g_lag = gm;
+        }
+        __syncthreads();
+        const int gm = rs->g_lag;
+        double wsum = 0.0;
+        for (int i = tid; i < 2 * a.w - 1; i += T) {
+            const int m = gm - (a.w - 1) + i;
+            if (m >= 0 && m < G::N) {
+                int ap, col;
+                G::cell_of_lag(m, ap, col);
+                if (col / S::CH == rank) {
+                    const float v = acc[ap * S::CH + (col - rank * S::CH)];
+                    wsum += (double)v * (double)v;
+                }
+            }
+        }
+        float dv = -1.f;
+        int dm = INT_MAX;
+        block_reduce<T>(dv, dm, wsum, rs);
+        target += R;
+        if (tid == 0) {
+            slots[rank].sum_win = wsum;
+            group_arrive(ctr);
+            group_spin(ctr, target);
+            if (rank == 0) {
+                double s_all = 0.0, s_win = 0.0;
+                for (int r = 0; r < R; ++r) {
+                    s_all += __ldcg(&slots[r].sum_all);
+                    s_win += __ldcg(&slots[r].sum_win);
+                }
+                Candidate c;
+                c.peak = rs->g_peak;
+                c.lag = rs->g_lag;
+                c.sum_all = s_all;
+                c.sum_win = s_win;
+                a.cand[(size_t)p * a.B + b] = c;
+            }
+        }
+        // the slots are rewritten at the end of the next row, K block barriers later: no extra barrier
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ launch glue
 template <class K, class A>
 static cudaError_t launch_clustered(K kern, const A& args, int units, int R, int T, size_t smem, cudaStream_t s) {
@@ -480,12 +637,27 @@ struct Variant {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(natural_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(search_kernel_coop<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(search_kernel_l2x<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(search_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
     }
     static cudaError_t launch_search_l2x(const SearchArgs& a, int clusters, cudaStream_t s) {
         return launch_clustered(search_kernel_l2x<Q, R, T, MINB>, a, clusters, R, T, Smem<Q, R>::search, s);
+    }
+    static cudaError_t launch_search_coop(const SearchArgs& a, int groups, cudaStream_t s) {
+        SearchArgs copy = a;
+        void* args[] = {&copy};
+        return cudaLaunchCooperativeKernel((const void*)search_kernel_coop<Q, R, T, MINB>, dim3((unsigned)(groups * R)),
+                                           dim3((unsigned)T), args, Smem<Q, R>::search, s);
+    }
+    static int max_groups_coop() {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel_coop<Q, R, T, MINB>, T, Smem<Q, R>::search) != cudaSuccess) { cudaGetLastError(); return 0; }
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return per_sm * sms / R;
     }
     static int max_clusters_l2x() {
         cudaLaunchConfig_t cfg = {};
@@ -519,7 +691,8 @@ struct Variant {
         return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, R>::transform,
                           &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
-                          (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf)};
+                          (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf),
+                          &launch_search_coop, &max_groups_coop};
     }
 };
 

@@ -3,6 +3,7 @@
 namespace gnss {
 const VariantOps* gnss_variants_q13(int* count) {
     static const VariantOps v[] = {
+        Variant<13, 8, 128, 4>::ops(),   // default (first match): fastest measured, profiles/r01
         Variant<13, 2, 512, 1>::ops(),
         Variant<13, 4, 256, 2>::ops(),
         Variant<13, 4, 512, 1>::ops(),

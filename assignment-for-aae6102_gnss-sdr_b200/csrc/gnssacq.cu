@@ -164,6 +164,9 @@ struct gnssacq_handle {
     float* d_surface = nullptr;
     cf* d_scratch = nullptr;
     int l2x_clusters = 0;          // > 0: use the L2-exchange persistent search kernel with this many clusters
+    int coop_groups = 0;           // > 0: use the cluster-free cooperative kernel with this many CTA groups
+    unsigned* d_group_ctr = nullptr;
+    Candidate* d_row_slots = nullptr;
     long long* d_sums = nullptr;
     double* d_means = nullptr;
     cf *d_fft_in = nullptr, *d_fft_out = nullptr;
@@ -241,7 +244,7 @@ int validate(const gnssacq_config* c, std::string& why) {
     if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
     for (int i = 0; i < c->n_prn; ++i)
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
-    if (c->exchange < 0 || c->exchange > 2) { why = "exchange must be 0 (auto), 1 (DSMEM) or 2 (L2)"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->exchange < 0 || c->exchange > 3) { why = "exchange must be 0 (auto), 1 (DSMEM), 2 (L2 + clusters) or 3 (L2 + cooperative groups)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
         why = "samples_per_ms must be 2000*Q (built: Q = 3, 13, 29 -> 6000, 26000, 58000)";
         return GNSSACQ_ERR_UNSUPPORTED_N;
@@ -303,7 +306,7 @@ int gnssacq_destroy(gnssacq_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
     cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
-    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     if (h->h_if) cudaFreeHost(h->h_if);
     if (h->h_res) cudaFreeHost(h->h_res);
@@ -389,19 +392,20 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     CUC(cudaMalloc(&h->d_res, h->P * sizeof(gnssacq_result)));
     CUC(cudaMalloc(&h->d_sums, 2 * sizeof(long long)));
     CUC(cudaMalloc(&h->d_means, 2 * sizeof(double)));
-    // auto: the L2 exchange wins where the DSMEM pull is bandwidth bound (N = 58 000, 4-CTA clusters);
-    // for the smaller transforms the two are within noise and DSMEM needs no scratch (profiles/r01).
-    const bool want_l2x = cfg->exchange == 2 || (cfg->exchange == 0 && Q >= 29);
-    if (want_l2x) {
-        int n = ops->max_clusters_l2x();
+    // exchange: 1 = DSMEM clusters, 2 = L2 buffer + clusters, 3 = L2 buffer + cooperative groups (no clusters).
+    // auto: cooperative groups for the two real front ends (fastest measured, profiles/r01), DSMEM for tiny N.
+    const int xmode = cfg->exchange ? cfg->exchange : (Q >= 13 ? 3 : 1);
+    if (xmode == 2 || xmode == 3) {
+        int n = xmode == 3 ? ops->max_groups_coop() : ops->max_clusters_l2x();
         if (n > h->P * h->B) n = h->P * h->B;
-        if (n > 0) {
-            h->l2x_clusters = n;
-            CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
-        } else if (cfg->exchange == 2) {
+        if (n <= 0) {
             gnssacq_destroy(h);
-            return fail(nullptr, GNSSACQ_ERR_CUDA, "L2-exchange search kernel cannot be made resident on this device");
+            return fail(nullptr, GNSSACQ_ERR_CUDA, "persistent search kernel cannot be made resident on this device");
         }
+        if (xmode == 3) h->coop_groups = n; else h->l2x_clusters = n;
+        CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
+        CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * sizeof(unsigned)));
+        CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
     if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
     CUC(cudaMallocHost(&h->h_if, h->if_bytes));
@@ -469,8 +473,16 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.cand = h->d_cand;
     sa.surface = h->d_surface;
     sa.scratch = h->d_scratch;
-    if (h->l2x_clusters > 0) CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));
-    else CU(h->ops->launch_search(sa, h->P * h->B, s));
+    sa.group_ctr = h->d_group_ctr;
+    sa.row_slots = h->d_row_slots;
+    if (h->coop_groups > 0) {
+        CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * sizeof(unsigned), s));
+        CU(h->ops->launch_search_coop(sa, h->coop_groups, s));
+    } else if (h->l2x_clusters > 0) {
+        CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));
+    } else {
+        CU(h->ops->launch_search(sa, h->P * h->B, s));
+    }
     h->launches += 1;
     CU(cudaEventRecord(h->ev[3], s));
     finalize_kernel<<<(h->P + 63) / 64, 64, 0, s>>>(h->d_cand, h->P, h->B, h->N, h->w, h->cfg.freq_min_hz,
@@ -519,8 +531,8 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
         st->n_bases = (int)h->base_freq.size();
         st->cluster_ctas = h->ops->R;
         st->threads = h->ops->T;
-        st->exchange = h->l2x_clusters > 0 ? 2 : 1;
-        st->resident_clusters = h->l2x_clusters;
+        st->exchange = h->coop_groups > 0 ? 3 : (h->l2x_clusters > 0 ? 2 : 1);
+        st->resident_clusters = h->coop_groups > 0 ? h->coop_groups : h->l2x_clusters;
     }
     return GNSSACQ_OK;
 }

@@ -309,7 +309,7 @@ def run_gpu(args, cfg):
             "data": "synthetic",
             "config": {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
                        "coh_ms": cfg["m"], "prns": 32, "cells": cells, "cell_blocks": cells * cfg["k"],
-                       "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2"}.get(st.exchange),
+                       "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2+clusters", 3: "l2+coop-groups"}.get(st.exchange),
                                   "resident_clusters": st.resident_clusters},
                        "sharding": f"PRN-major, {n_local} PRNs on rank 0",
                        "l2": "flushed between steps (256 MiB device memset, outside the per-step event pair)",

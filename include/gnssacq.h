@@ -61,7 +61,9 @@ typedef struct gnssacq_config {
     int32_t keep_surface;     /* debug: also keep the freq_num x samples_per_ms power surface of
                                  every PRN in HBM for gnssacq_read_surface (costs HBM + bandwidth) */
     int32_t exchange;         /* engine variant: how the CTAs of a transform exchange rows before the last
-                                 pass.  0 = auto, 1 = distributed shared memory, 2 = L2-resident buffer */
+                                 pass.  0 = auto, 1 = distributed shared memory (clusters), 2 = L2-resident
+                                 buffer (persistent clusters), 3 = L2-resident buffer, cooperative CTA
+                                 groups without clusters (uses every SM) */
 } gnssacq_config;
 
 /* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */
@@ -89,8 +91,8 @@ typedef struct gnssacq_stats {
     int32_t n_bases;          /* distinct forward transforms per block after the bin-shift identity */
     int32_t cluster_ctas;     /* engine variant actually used */
     int32_t threads;
-    int32_t exchange;         /* 1 = DSMEM, 2 = L2 */
-    int32_t resident_clusters;/* persistent clusters of the L2-exchange search kernel (0 for DSMEM) */
+    int32_t exchange;         /* 1 = DSMEM, 2 = L2 + clusters, 3 = L2 + cooperative groups */
+    int32_t resident_clusters;/* persistent clusters / CTA groups of the search kernel (0 for DSMEM) */
 } gnssacq_stats;
 
 typedef struct gnssacq_handle gnssacq_handle;
