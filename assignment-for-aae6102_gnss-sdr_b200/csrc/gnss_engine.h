@@ -92,8 +92,13 @@ template <int Q, int R, class Loader>
 GNSS_HD void pass1_compute(int task, int rank, const Loader& ld, cf (&z)[Q]) {
     using S = Split<Q, R>;
     const int al = task / 125, b = task - al * 125;
-    ld.template load<Q>(rank * S::A + al, b, z);
-    dft_odd<Q>(z);
+    if constexpr (Loader::kStreams) {
+        const auto ctx = ld.template begin<Q>(rank * S::A + al, b);
+        dft_odd_stream<Q>([&](auto cc) { return ld.template at<Q, decltype(cc)::value>(ctx); }, z);
+    } else {
+        ld.template load<Q>(rank * S::A + al, b, z);
+        dft_odd<Q>(z);
+    }
 }
 // store half: D[a_local][c'][b]
 template <int Q, int R>
@@ -229,6 +234,20 @@ struct SearchLoader {
                                     // [16][2Q-1][125] (plane c and c+Q hold the same data), so the
                                     // rotation (c - sc) mod Q is a plain offset
     int sa, sb, sc;                 // bin shift in Good coordinates
+    static constexpr bool kStreams = true;
+    struct Ctx { const cf* pc; const cf* px; };
+    template <int Q>
+    GNSS_HD Ctx begin(int a, int b) const {
+        const int as = (a - sa) & 15;
+        int bs = b - sb; if (bs < 0) bs += 125;
+        const int c0 = (sc == 0) ? 0 : Q - sc;
+        Ctx c;
+        c.pc = cc + (a * Q) * 125 + b;
+        c.px = x + (as * (2 * Q - 1) + c0) * 125 + bs;
+        return c;
+    }
+    template <int Q, int C>
+    GNSS_HD cf at(const Ctx& c) const { return cmul(ld_ro(c.pc + C * 125), ld_ro(c.px + C * 125)); }
     template <int Q>
     GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
         const int as = (a - sa) & 15;
@@ -293,6 +312,7 @@ struct SpectrumStorer {
 
 // ---- code replica loader (K0): real +-1 samples, natural order ----
 struct CodeLoader {
+    static constexpr bool kStreams = false;
     const int8_t* __restrict__ scode;   // N samples of this PRN (acquisition.m:51)
     template <int Q>
     GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
@@ -319,6 +339,7 @@ GNSS_HD void carrier_sincos(double f_hz, double fs_hz, long long n1 /*1-based sa
 }
 
 struct WipeoffLoader {
+    static constexpr bool kStreams = false;
     const void* __restrict__ raw;   // start of this coherent block (sample 0 of the block)
     int data_type;                  // 1 real, 2 I/Q          (file.dataType)
     int precision;                  // 1 int8, 2 int16        (file.dataPrecision)

@@ -21,6 +21,7 @@ namespace gnss {
 namespace cg = cooperative_groups;
 
 struct NaturalLoader {
+    static constexpr bool kStreams = false;
     const cf* __restrict__ in;
     template <int Q>
     __device__ __forceinline__ void load(int a, int b, cf (&z)[Q]) const {

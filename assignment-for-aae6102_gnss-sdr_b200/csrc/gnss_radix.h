@@ -45,6 +45,44 @@ GNSS_HD void dft_odd(cf (&v)[Q]) {
     });
 }
 
+// Same transform, input-major ("streaming") form: inputs are fetched pair by pair through `get`
+// (get(integral_constant<int,C>) -> cf) and folded into all (Q-1)/2 output accumulators at once, so the
+// arithmetic on the first pairs overlaps the memory latency of the later ones.  4*H accumulators live.
+template <int Q, class Get>
+GNSS_HD void dft_odd_stream(Get&& get, cf (&v)[Q]) {
+    static_assert(Q % 2 == 1 && Q >= 3, "odd length");
+    constexpr int H = (Q - 1) / 2;
+    const cf x0 = get(std::integral_constant<int, 0>{});
+    float cx[H + 1], cy[H + 1], sx[H + 1], sy[H + 1];
+    static_for<1, H + 1>([&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        cx[K] = x0.x; cy[K] = x0.y; sx[K] = 0.f; sy[K] = 0.f;
+    });
+    cf s0 = x0;
+    static_for<1, H + 1>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        const cf p = get(std::integral_constant<int, J>{});
+        const cf q = get(std::integral_constant<int, Q - J>{});
+        const cf a = cadd(p, q), b = csub(p, q);
+        s0 = cadd(s0, a);
+        static_for<1, H + 1>([&](auto kc) {
+            constexpr int K = decltype(kc)::value;
+            constexpr int T = (J * K) % Q;
+            constexpr float c = Tw<T, Q>::c, s = Tw<T, Q>::s;
+            cx[K] += c * a.x;
+            cy[K] += c * a.y;
+            sx[K] += s * b.x;
+            sy[K] += s * b.y;
+        });
+    });
+    v[0] = s0;
+    static_for<1, H + 1>([&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        v[K] = mk(cx[K] + sy[K], cy[K] - sx[K]);
+        v[Q - K] = mk(cx[K] - sy[K], cy[K] + sx[K]);
+    });
+}
+
 GNSS_HD void dft4(cf& x0, cf& x1, cf& x2, cf& x3) {
     const cf t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
     x0 = cadd(t0, t2);
