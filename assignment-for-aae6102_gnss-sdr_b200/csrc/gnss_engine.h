@@ -378,6 +378,72 @@ struct WipeoffLoader {
     }
 };
 
+// ---- fine-frequency loader (acquisition.m:104-110): code wipe-off of the long block, decimated by L,
+//      modulated for residue r of the zero-padded spectrum.  The length-F (F = K*L*N) spectrum of the
+//      L*N code-stripped samples s[n] is  X[K*(q1 + N*q2) + r] = sum_{n2<L} W_L^{n2 q2} W_{LN}^{n2 q1}
+//      DFT_N{ s[L*n1 + n2] * exp(-2*pi*i*(L*n1+n2)*r/F) }[q1] : K*L transforms of N points. ----
+struct FineLoader {
+    static constexpr bool kStreams = false;
+    const void* __restrict__ raw;        // (L+1) ms block as read at acquisition.m:91/96
+    const uint16_t* __restrict__ chip;   // [L*N] chip index of sample t (acquisition.m:104-105), 0-based
+    const int8_t* __restrict__ ca;       // [1023] C/A chips of this SV
+    int data_type, precision;
+    float mean_i, mean_q;                // int16 path (acquisition.m:94)
+    int start;                           // 0-based first sample = N - codedelay - 1 (acquisition.m:106)
+    int L, n2, r;
+    long long F;                         // fftlength = L*N*datalen (acquisition.m:108)
+    template <int Q>
+    GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
+        static_for<0, Q>([&](auto c_) {
+            constexpr int C = decltype(c_)::value;
+            const int n1 = Geo<Q>::good(a, b, C);
+            const long long n = (long long)L * n1 + n2;
+            const long long idx = (long long)start + n;
+            float xi, xq;
+            if (precision == 2) {
+                const int16_t* p = (const int16_t*)raw;
+                xi = (float)p[2 * idx] - mean_i;
+                xq = (float)p[2 * idx + 1] - mean_q;
+            } else if (data_type == 2) {
+                const int8_t* p = (const int8_t*)raw;
+                xi = (float)p[2 * idx];
+                xq = (float)p[2 * idx + 1];
+            } else {
+                xi = (float)((const int8_t*)raw)[idx];
+                xq = 0.f;
+            }
+            const float cv = (float)ca[chip[n]];
+            xi *= cv;
+            xq *= cv;
+            const long long m = (n * (long long)r) % F;          // exact phase numerator
+            const double fr = (double)m / (double)F;
+            float co, si;
+#if defined(__CUDA_ARCH__)
+            sincospif((float)(2.0 * fr), &si, &co);
+#else
+            co = (float)cos(2.0 * 3.14159265358979323846 * fr);
+            si = (float)sin(2.0 * 3.14159265358979323846 * fr);
+#endif
+            // (xi + i xq) * (co - i si)
+            z[C] = mk(xi * co + xq * si, xq * co - xi * si);
+        });
+    }
+};
+
+// natural-order store: out[frequency index] (used by the fine stage and the FFT test hook)
+struct NaturalStorerHD {
+    cf* __restrict__ out;
+    template <int Q, int R>
+    GNSS_HD void store2(int col, int, const cf (&w0)[16], const cf (&w1)[16]) {
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int AP = (I / 4) + 4 * (I % 4);
+            out[Geo<Q>::lag_of(AP, col)] = w0[I];
+            if (col + 1 < Geo<Q>::ROW) out[Geo<Q>::lag_of(AP, col + 1)] = w1[I];
+        });
+    }
+};
+
 // ================================================================== row-end helpers
 struct RowPeak {
     float peak;        // max accumulated power

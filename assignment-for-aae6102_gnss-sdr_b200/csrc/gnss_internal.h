@@ -50,6 +50,18 @@ struct NaturalArgs {
     cf* out;               // [units][N] natural order
 };
 
+// fine-frequency stage (acquisition.m:83-127): K*L decimated N-point transforms per acquired SV
+struct FineArgs {
+    const void* raw;             // device copy of the (L+1) ms block
+    const uint16_t* chip;        // [L*N]
+    const int8_t* ca;            // [n_sv][1023]
+    const int* start;            // [n_sv] N - codedelay - 1
+    const double* means;         // [2] int16 path, else nullptr
+    int data_type, precision, L, K;
+    long long F;
+    cf* u;                       // [n_sv][K][L][N] natural order
+};
+
 struct VariantOps {
     int Q, R, T;
     size_t smem_search, smem_transform;
@@ -57,6 +69,7 @@ struct VariantOps {
     cudaError_t (*launch_code)(const CodeArgs&, int units, cudaStream_t);
     cudaError_t (*launch_wipe)(const WipeArgs&, int units, cudaStream_t);
     cudaError_t (*launch_natural)(const NaturalArgs&, int units, cudaStream_t);
+    cudaError_t (*launch_fine)(const FineArgs&, int units, cudaStream_t);
     cudaError_t (*launch_search)(const SearchArgs&, int rows, cudaStream_t);
     // L2-exchange persistent variant: `clusters` co-resident clusters loop over the rows
     cudaError_t (*launch_search_l2x)(const SearchArgs&, int clusters, cudaStream_t);

@@ -226,6 +226,31 @@ __global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
     unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
 }
 
+// fine-frequency transforms: unit = ((sv * K) + r) * L + n2
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) fine_kernel(FineArgs a) {
+    GNSS_KERNEL_PROLOGUE
+    cf* tw = D + S::D_ELEMS;
+    fill_tw125(tw, tid, T);
+    __syncthreads();
+    const int n2 = unit % a.L, r = (unit / a.L) % a.K, sv = unit / (a.L * a.K);
+    FineLoader ld;
+    ld.raw = a.raw;
+    ld.chip = a.chip;
+    ld.ca = a.ca + (size_t)sv * 1023;
+    ld.data_type = a.data_type;
+    ld.precision = a.precision;
+    ld.mean_i = a.means ? (float)a.means[0] : 0.f;
+    ld.mean_q = a.means ? (float)a.means[1] : 0.f;
+    ld.start = a.start[sv];
+    ld.L = a.L;
+    ld.n2 = n2;
+    ld.r = r;
+    ld.F = a.F;
+    NaturalStorerHD st{a.u + (size_t)unit * G::N};
+    unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
+}
+
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
     GNSS_KERNEL_PROLOGUE
@@ -638,6 +663,8 @@ struct Variant {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(natural_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fine_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(search_kernel_coop<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(search_kernel_l2x<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
@@ -685,12 +712,15 @@ struct Variant {
     static cudaError_t launch_natural(const NaturalArgs& a, int units, cudaStream_t s) {
         return launch_clustered(natural_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
     }
+    static cudaError_t launch_fine(const FineArgs& a, int units, cudaStream_t s) {
+        return launch_clustered(fine_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+    }
     static cudaError_t launch_search(const SearchArgs& a, int rows, cudaStream_t s) {
         return launch_clustered(search_kernel<Q, R, T, MINB>, a, rows, R, T, Smem<Q, R>::search, s);
     }
     static constexpr VariantOps ops() {
         return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, R>::transform,
-                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_search,
+                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_fine, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
                           (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf),
                           &launch_search_coop, &max_groups_coop};

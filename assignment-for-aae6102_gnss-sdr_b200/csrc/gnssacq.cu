@@ -121,6 +121,61 @@ __global__ void means_kernel(const long long* __restrict__ sums, long long n_pai
     means[1] = (double)sums[1] / (double)n_pairs;
 }
 
+// Fine-frequency combine (acquisition.m:110-116): for every (sv, r, q1) the L decimated spectra are
+// twiddled and combined by a direct DFT-L, giving X[K*(q1 + N*q2) + r]; |X|^2 feeds a first-index
+// argmax in the reference's index order (after fftshift for I/Q data), packed as
+// (float bits << 32) | (0xFFFFFFFF - index) so one 64-bit max implements value-then-lowest-index.
+__global__ void __launch_bounds__(256) fine_combine_kernel(const cf* __restrict__ u, int K, int L, int N, long long F,
+                                                           int shifted, unsigned long long* __restrict__ best) {
+    __shared__ cf wl[16];
+    __shared__ unsigned long long wbest[8];
+    const int r = blockIdx.y, sv = blockIdx.z;
+    if (threadIdx.x < L) {
+        double s, c;
+        sincospi(-2.0 * (double)threadIdx.x / (double)L, &s, &c);
+        wl[threadIdx.x] = mk((float)c, (float)s);
+    }
+    __syncthreads();
+    const int q1 = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (q1 < N) {
+        cf v[16];
+        const cf* base = u + ((size_t)(sv * K + r) * L) * N + q1;
+        const long long LN = (long long)L * N;
+        for (int n2 = 0; n2 < L; ++n2) {
+            const cf x = base[(size_t)n2 * N];
+            const long long m = ((long long)n2 * q1) % LN;
+            float si, co;
+            sincospif((float)(2.0 * (double)m / (double)LN), &si, &co);
+            v[n2] = mk(x.x * co + x.y * si, x.y * co - x.x * si);       // x * exp(-2 pi i m / LN)
+        }
+        for (int q2 = 0; q2 < L; ++q2) {
+            float yr = 0.f, yi = 0.f;
+            for (int n2 = 0; n2 < L; ++n2) {
+                const cf w = wl[(n2 * q2) % L];
+                yr += v[n2].x * w.x - v[n2].y * w.y;
+                yi += v[n2].x * w.y + v[n2].y * w.x;
+            }
+            const long long k = (long long)K * ((long long)q1 + (long long)N * q2) + r;
+            const long long j = shifted ? (k + F / 2) % F : k;
+            const float pw = yr * yr + yi * yi;
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(pw) << 32) |
+                                            (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
+            key = cand > key ? cand : key;
+        }
+    }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, key, off);
+        key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) key = wbest[w] > key ? wbest[w] : key;
+        atomicMax(best + sv, key);
+    }
+}
+
 // FP32 FMA peak probe: 16 independent FFMA chains per thread, 8 CTAs x 256 threads per SM.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
     float v[16];
@@ -563,6 +618,94 @@ int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out) {
     CU(cudaStreamSynchronize(h->stream));
     const size_t n = (size_t)h->B * h->N;
     CU(cudaMemcpy(out, h->d_surface + (size_t)prn_index * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_fine_frequency(gnssacq_handle* h, const void* if_long, size_t nbytes, int32_t L, int32_t n_sv,
+                           const int32_t* prn, const int32_t* code_phase, double* out_hz) {
+    if (!h || !if_long || !prn || !code_phase || !out_hz) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (n_sv == 0) return GNSSACQ_OK;
+    if (L < 1 || L > 16 || n_sv < 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "L must be 1..16, n_sv >= 0");
+    const gnssacq_config& c = h->cfg;
+    const size_t bps = (size_t)c.data_type * c.data_precision;
+    const size_t need = (size_t)(L + 1) * h->N * bps;
+    if (nbytes < need) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "fine-frequency stage needs (L+1) ms of IF (acquisition.m:91/96)");
+    for (int i = 0; i < n_sv; ++i)
+        if (prn[i] < 1 || prn[i] > 51 || code_phase[i] < 0 || code_phase[i] >= h->N)
+            return fail(h, GNSSACQ_ERR_INVALID_ARG, "PRN or code phase out of range");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int N = h->N, K = h->K;
+    const long long LN = (long long)L * N, F = LN * K;                          // acquisition.m:108
+    if (F > 0xFFFFFFFFll) return fail(h, GNSSACQ_ERR_INVALID_ARG, "fftlength exceeds 2^32");
+
+    void* d_raw = nullptr; uint16_t* d_chip = nullptr; int8_t* d_ca = nullptr; int* d_start = nullptr;
+    cf* d_u = nullptr; unsigned long long* d_best = nullptr;
+    auto cleanup = [&]() { cudaFree(d_raw); cudaFree(d_chip); cudaFree(d_ca); cudaFree(d_start); cudaFree(d_u); cudaFree(d_best); };
+#define CUF(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) { cleanup(); return fail(h, GNSSACQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
+    } while (0)
+    // host tables: chip index of sample t (acquisition.m:104-105, same double arithmetic), C/A chips, start offsets
+    std::vector<uint16_t> chip((size_t)LN);
+    {
+        const double inv_fs = 1.0 / c.fs_hz, inv_fc = 1.0 / c.code_hz;
+        const double codelength = c.code_hz * 1e-3;                             // initParameters.m:47
+        for (long long t = 1; t <= LN; ++t) {
+            const double idx = std::floor((inv_fs * (double)t) / inv_fc);
+            chip[(size_t)(t - 1)] = (uint16_t)std::fmod(idx, codelength);       // rem(.)+1, 0-based here
+        }
+    }
+    std::vector<int8_t> ca((size_t)n_sv * 1023);
+    std::vector<int> start(n_sv);
+    for (int i = 0; i < n_sv; ++i) {
+        ca_chips(prn[i], ca.data() + (size_t)i * 1023);
+        start[i] = N - code_phase[i] - 1;                                       // acquisition.m:106 (1-based N-codedelay)
+    }
+    const int chunk = n_sv < 4 ? n_sv : 4;                                      // SVs per pass (bounds the scratch to ~0.4 GB)
+    CUF(cudaMalloc(&d_raw, need));
+    CUF(cudaMalloc(&d_chip, chip.size() * sizeof(uint16_t)));
+    CUF(cudaMalloc(&d_ca, ca.size()));
+    CUF(cudaMalloc(&d_start, n_sv * sizeof(int)));
+    CUF(cudaMalloc(&d_best, n_sv * sizeof(unsigned long long)));
+    CUF(cudaMalloc(&d_u, (size_t)chunk * K * L * N * sizeof(cf)));
+    CUF(cudaMemcpyAsync(d_raw, if_long, need, cudaMemcpyHostToDevice, s));
+    CUF(cudaMemcpyAsync(d_chip, chip.data(), chip.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    CUF(cudaMemcpyAsync(d_ca, ca.data(), ca.size(), cudaMemcpyHostToDevice, s));
+    CUF(cudaMemcpyAsync(d_start, start.data(), n_sv * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUF(cudaMemsetAsync(d_best, 0, n_sv * sizeof(unsigned long long), s));
+    const double* means = nullptr;
+    if (c.data_precision == 2) {                                                // acquisition.m:92-94
+        const long long pairs = (long long)(L + 1) * N;
+        CUF(cudaMemsetAsync(h->d_sums, 0, 2 * sizeof(long long), s));
+        sum_int16_kernel<<<296, 256, 0, s>>>((const int16_t*)d_raw, pairs, h->d_sums);
+        means_kernel<<<1, 1, 0, s>>>(h->d_sums, pairs, h->d_means);
+        CUF(cudaGetLastError());
+        means = h->d_means;
+    }
+    for (int first = 0; first < n_sv; first += chunk) {
+        const int n = (n_sv - first) < chunk ? (n_sv - first) : chunk;
+        FineArgs fa;
+        fa.raw = d_raw; fa.chip = d_chip; fa.ca = d_ca + (size_t)first * 1023; fa.start = d_start + first;
+        fa.means = means; fa.data_type = c.data_type; fa.precision = c.data_precision;
+        fa.L = L; fa.K = K; fa.F = F; fa.u = d_u;
+        CUF(h->ops->launch_fine(fa, n * K * L, s));
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)K, (unsigned)n);
+        fine_combine_kernel<<<grid, 256, 0, s>>>(d_u, K, L, N, F, c.data_type == 2 ? 1 : 0, d_best + first);
+        CUF(cudaGetLastError());
+    }
+    std::vector<unsigned long long> best(n_sv);
+    CUF(cudaMemcpyAsync(best.data(), d_best, n_sv * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUF(cudaStreamSynchronize(s));
+#undef CUF
+    cleanup();
+    for (int i = 0; i < n_sv; ++i) {
+        const double idx = (double)(0xFFFFFFFFu - (unsigned)(best[i] & 0xFFFFFFFFull)) + 1.0;   // 1-based FreqPeakIndex (:116)
+        double fine = idx * (c.fs_hz / (double)F);                                                // :117
+        if (c.data_type == 2) fine = -idx * (c.fs_hz / (double)F) + c.fs_hz / 2.0;                // :119
+        out_hz[i] = fine;
+    }
     return GNSSACQ_OK;
 }
 

@@ -60,7 +60,7 @@ def read_if_bytes(file, signal, n_ms: int) -> bytes:
     return file.fid.read(nbytes * n_ms)
 
 
-def acquisition(file, signal, acq, *, coh_ms: int = 1, verbose: bool = True,
+def acquisition(file, signal, acq, *, coh_ms: int = 1, verbose: bool = True, fine: bool = True,
                 return_rows: bool = False, searcher: Optional[api.Searcher] = None):
     cfg = searcher.cfg if searcher is not None else config_from_structs(file, signal, acq, coh_ms=coh_ms)
     s = searcher if searcher is not None else get_searcher(cfg)
@@ -74,8 +74,7 @@ def acquisition(file, signal, acq, *, coh_ms: int = 1, verbose: bool = True,
         "SNR": np.array([r.snr_db for r in hit], dtype=np.float64),
         "Doppler": np.array([r.doppler_hz for r in hit], dtype=np.float64),
         "codedelay": np.array([r.code_phase for r in hit], dtype=np.float64),
-        # fine-frequency stage (acquisition.m:83-127) is outside this path: NaN per acquired SV
-        "fineFreq": np.array([r.fine_freq_hz for r in hit], dtype=np.float64),
+        "fineFreq": np.array([], dtype=np.float64) if fine else np.full(len(hit), np.nan),
     }
     if verbose:
         for r in hit:                                                            # :76-77
@@ -83,6 +82,16 @@ def acquisition(file, signal, acq, *, coh_ms: int = 1, verbose: bool = True,
                   f"Raw Doppler = {int(r.doppler_hz):5d} ")
         if not hit:
             print("No satellites acquired. Check parameter settings ... ")      # :85
+    if fine and hit:                                                             # :88-126, on the GPU
+        if verbose:
+            print("Now refining Doppler freq... ")
+        long_raw = read_if_bytes(file, signal, int(acq.L) + 1)                   # :89-100
+        Acquired["fineFreq"] = s.fine_frequency(long_raw, int(acq.L), [r.prn for r in hit],
+                                                [r.code_phase for r in hit])
+        if verbose:
+            for r, ff in zip(hit, Acquired["fineFreq"]):                         # :123-125
+                print(f" SV[{r.prn:2d}] SNR = {r.snr_db:2.2f}, Code phase = {r.code_phase:5d}, "
+                      f"Raw Doppler = {int(r.doppler_hz):5d}, Fine Doppler = {ff - signal.IF:5f} ")
     if return_rows:
         return Acquired, rows
     return Acquired

@@ -72,7 +72,7 @@ EXPORTS = (
     "gnssacq_version", "gnssacq_config_default", "gnssacq_if_bytes", "gnssacq_create",
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
-    "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops",
+    "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
 )
 
 
@@ -101,6 +101,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_code_replica.argtypes = [C.POINTER(Config), C.c_int32, vp]
     lib.gnssacq_read_surface.argtypes = [vp, C.c_int32, vp]
     lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
+    lib.gnssacq_fine_frequency.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32, vp, vp, vp]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
@@ -234,6 +235,18 @@ class Searcher:
         self._check(lib.gnssacq_fetch_results(self._h, out, C.byref(st)))
         self.last_stats = st
         return list(out)
+
+    def fine_frequency(self, if_long, L: int, prns: Sequence[int], code_phases: Sequence[int]) -> np.ndarray:
+        """acquisition.m:89-121 on the GPU: `if_long` = (L+1) ms of raw IF bytes, one fineFreq per SV."""
+        buf = np.frombuffer(if_long, dtype=np.uint8) if not isinstance(if_long, np.ndarray) else if_long
+        buf = np.ascontiguousarray(buf)
+        p = np.ascontiguousarray(prns, dtype=np.int32)
+        cp = np.ascontiguousarray(code_phases, dtype=np.int32)
+        out = np.full(p.size, np.nan, dtype=np.float64)
+        if p.size:
+            self._check(lib.gnssacq_fine_frequency(self._h, buf.ctypes.data, buf.nbytes, int(L), int(p.size),
+                                                   p.ctypes.data, cp.ctypes.data, out.ctypes.data))
+        return out
 
     def read_surface(self, prn_index: int) -> np.ndarray:
         out = np.empty((self.cfg.freq_num, self.cfg.samples_per_ms), dtype=np.float32)

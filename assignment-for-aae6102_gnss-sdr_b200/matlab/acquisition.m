@@ -32,7 +32,14 @@ for k = 1:size(hit, 1)
     fprintf(' SV[%2d] SNR = %2.2f, Code phase = %5d, Raw Doppler = %5d \n ', ...
         hit(k, 1), hit(k, 8), hit(k, 3), hit(k, 5));
 end
-% Fine-frequency refinement is a separate stage of the reference (not part of the search path
-% this library replaces).  Until it has its own GPU kernel the coarse value stands in:
-Acquired.fineFreq = signal.IF + Acquired.Doppler;
+% Fine-frequency refinement, also on the GPU: the gateway takes the (L+1) ms block and the acquired
+% (PRN, code phase) pairs and returns the absolute carrier frequency of each.
+fprintf('Now refining Doppler freq... \n ');
+fseek(file.fid, file.skip * bytesPerMs, 'bof');
+longraw = fread(file.fid, signal.Sample * file.dataType * (acq.L + 1), kinds{file.dataPrecision});
+Acquired.fineFreq = gnssacq_mex(longraw, cfg, acq.L, Acquired.sv, Acquired.codedelay);
+for k = 1:numel(Acquired.sv)
+    fprintf(' SV[%2d] SNR = %2.2f, Code phase = %5d, Raw Doppler = %5d, Fine Doppler = %5f \n ', ...
+        Acquired.sv(k), Acquired.SNR(k), Acquired.codedelay(k), Acquired.Doppler(k), Acquired.fineFreq(k) - signal.IF);
+end
 end

@@ -1,6 +1,7 @@
 /* gnssacq_mex.c -- MEX gateway from MATLAB to libgnssacq.so (include/gnssacq.h).
  *
- *   rows = gnssacq_mex(raw_int8_or_int16, cfg)
+ *   rows     = gnssacq_mex(raw_int8_or_int16, cfg)                        coarse search
+ *   fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay)                 fine-frequency stage
  *
  * `raw` is the block acquisition.m:29/34 reads, passed as int8 (or int16) WITHOUT conversion to
  * double; `cfg` is a scalar struct whose fields are named after gnssacq_config.  Returns an
@@ -44,7 +45,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     double* out;
     int rc, i;
 
-    if (nrhs != 2 || !mxIsStruct(prhs[1])) fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg)");
+    if ((nrhs != 2 && nrhs != 5) || !mxIsStruct(prhs[1]))
+        fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg) | fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay)");
     if (!(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
 
     gnssacq_config_default(&c);
@@ -80,6 +82,22 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     }
 
     nbytes = mxGetNumberOfElements(prhs[0]) * mxGetElementSize(prhs[0]);
+    if (nrhs == 5) {                                   /* fine-frequency stage (acquisition.m:83-127) */
+        int n_sv = (int)mxGetNumberOfElements(prhs[3]);
+        const double* svd = mxGetPr(prhs[3]);
+        const double* cdd = mxGetPr(prhs[4]);
+        int32_t* sv = (int32_t*)mxMalloc(sizeof(int32_t) * (size_t)(n_sv + 1));
+        int32_t* cd = (int32_t*)mxMalloc(sizeof(int32_t) * (size_t)(n_sv + 1));
+        if ((int)mxGetNumberOfElements(prhs[4]) != n_sv) fail(GNSSACQ_ERR_INVALID_ARG, "sv and codedelay differ in length");
+        for (i = 0; i < n_sv; ++i) { sv[i] = (int32_t)svd[i]; cd[i] = (int32_t)cdd[i]; }
+        plhs[0] = mxCreateDoubleMatrix(1, (mwSize)n_sv, mxREAL);
+        rc = gnssacq_fine_frequency(g_handle, mxGetData(prhs[0]), nbytes, (int32_t)mxGetScalar(prhs[2]), n_sv,
+                                    sv, cd, mxGetPr(plhs[0]));
+        mxFree(sv);
+        mxFree(cd);
+        if (rc != GNSSACQ_OK) fail(rc, gnssacq_last_error(g_handle));
+        return;
+    }
     rows = (gnssacq_result*)mxMalloc(sizeof(gnssacq_result) * (size_t)c.n_prn);
     rc = gnssacq_search(g_handle, mxGetData(prhs[0]), nbytes, rows, NULL);
     if (rc != GNSSACQ_OK) { mxFree(rows); fail(rc, gnssacq_last_error(g_handle)); }

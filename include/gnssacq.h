@@ -76,7 +76,7 @@ typedef struct gnssacq_result {
     double peak;              /* acquisition.m:63 */
     double noise_meansq;      /* denominator of acquisition.m:67-68 */
     double snr_db;            /* acquisition.m:67 */
-    double fine_freq_hz;      /* NaN: the fine-frequency stage (acquisition.m:83-127) is not on this path */
+    double fine_freq_hz;      /* NaN here; filled by gnssacq_fine_frequency (acquisition.m:83-127) */
 } gnssacq_result;
 
 /* Device-side timings of the last search (CUDA events on the handle's stream), milliseconds. */
@@ -137,6 +137,14 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
  * (`d_out_rows`, n_prn * sizeof(gnssacq_result) bytes) -- e.g. the send buffer of the NCCL
  * all-gather that assembles the per-rank PRN shards.  Stream-ordered; no host synchronisation. */
 int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if_samples, size_t nbytes, void* d_out_rows);
+
+/* Fine-frequency stage (replaces acquisition.m:89-121).  `if_long` is the (L+1) ms block
+ * acquisition.m:91/96 reads from the same file offset (host memory); for each of the n_sv acquired SVs
+ * (prn[i], code_phase[i] = Acquired.codedelay) the code-stripped L ms are zero-padded to
+ * fftlength = L*samples_per_ms*noncoh_blocks and the spectral peak gives out_hz[i] = Acquired.fineFreq
+ * (absolute Hz; for I/Q data  -idx*(Fs/fftlength) + Fs/2  with the reference's 1-based idx). */
+int gnssacq_fine_frequency(gnssacq_handle* h, const void* if_long, size_t nbytes, int32_t L, int32_t n_sv,
+                           const int32_t* prn, const int32_t* code_phase, double* out_hz);
 
 /* ---- table generators (host side, replace generateCAcode.m and acquisition.m:50-51) ---- */
 int gnssacq_ca_code(int32_t prn, int8_t out_chips[1023]);

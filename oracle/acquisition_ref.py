@@ -207,8 +207,11 @@ def coarse_search(raw: np.ndarray, signal, acq, prns: Iterable[int] = range(1, 3
 
 
 # --------------------------------------------------------------------------- fine frequency
-def fine_frequency(longraw: np.ndarray, file, signal, acq, prn: int, codedelay: int) -> float:
-    """acquisition.m:102-121 for one acquired SV.  ``longraw`` = (L+1) ms read as in :89-100."""
+def fine_frequency(longraw: np.ndarray, file, signal, acq, prn: int, codedelay: int, *, detail: bool = False):
+    """acquisition.m:102-121 for one acquired SV.  ``longraw`` = (L+1) ms read as in :89-100.
+
+    ``detail=True`` also returns (1-based peak index, peak magnitude, best other magnitude) so tests can
+    apply the floating-point tie tolerance."""
     n = int(signal.Sample)
     ca = generate_ca_code(prn)                                               # :103
     t = np.arange(1, acq.L * n + 1, dtype=np.float64)
@@ -226,6 +229,12 @@ def fine_frequency(longraw: np.ndarray, file, signal, acq, prn: int, codedelay: 
     fine = idx * (signal.Fs / fftlen)                                        # :117
     if file.dataType == 2:
         fine = -idx * (signal.Fs / fftlen) + signal.Fs / 2                   # :119
+    if detail:
+        sel = spec[:half * 2]
+        pk = float(sel[idx - 1])
+        rest = sel.copy()
+        rest[idx - 1] = -np.inf
+        return float(fine), idx, pk, float(rest.max())
     return float(fine)
 
 

@@ -95,6 +95,21 @@ static int search_row(const cf* cc, const cf* x_blocks, int K, int shift, float*
     return 0;
 }
 
+template <int Q, int R>
+static int fine_unit(const void* raw, const uint16_t* chip, const int8_t* ca, int data_type, int precision,
+                     float mi, float mq, int start, int L, int n2, int r, long long F, cf* out) {
+    using S = Split<Q, R>;
+    std::vector<std::vector<cf>> D(R, std::vector<cf>(S::D_ELEMS));
+    auto tw = make_tw125();
+    FineLoader ld;
+    ld.raw = raw; ld.chip = chip; ld.ca = ca; ld.data_type = data_type; ld.precision = precision;
+    ld.mean_i = mi; ld.mean_q = mq; ld.start = start; ld.L = L; ld.n2 = n2; ld.r = r; ld.F = F;
+    NaturalStorerHD st[R];
+    for (int k = 0; k < R; ++k) st[k] = NaturalStorerHD{out};
+    run_unit<Q, R>(ld, st, D, tw);
+    return 0;
+}
+
 template <int Q>
 static void gx_to_natural(const cf* g, cf* nat) {   // c-extended layout [16][2Q-1][125]; also checks the duplicate planes
     using G = Geo<Q>;
@@ -136,6 +151,11 @@ int emu_wipe_spectrum(int Q, int R, const void* raw, int data_type, int precisio
 int emu_search_row(int Q, int R, const float* cc, const float* x_blocks, int K, int shift,
                    float* acc_by_lag) {
     ALL((search_row<QQ, RR>((const cf*)cc, (const cf*)x_blocks, K, shift, acc_by_lag)))
+    return -2;
+}
+int emu_fine_unit(int Q, int R, const void* raw, const uint16_t* chip, const int8_t* ca, int data_type,
+                  int precision, float mi, float mq, int start, int L, int n2, int r, long long F, float* out) {
+    ALL((fine_unit<QQ, RR>(raw, chip, ca, data_type, precision, mi, mq, start, L, n2, r, F, (cf*)out)))
     return -2;
 }
 int emu_gx_to_natural(int Q, const float* g, float* nat) {

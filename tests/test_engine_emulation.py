@@ -72,3 +72,29 @@ def test_engine_passes_against_numpy(emu, Q, R):
             want += np.abs(np.fft.ifft(cfft * np.conj(np.fft.fft(t1)))) ** 2
         assert np.abs(acc - want).max() <= 5e-6 * want.max()
         assert int(acc.argmax()) == int(want.argmax())
+
+
+def test_fine_frequency_loader_against_numpy(emu):
+    """FineLoader + natural store: one decimated, modulated N-point transform of the code-stripped long block."""
+    Q, R, L, K = 3, 2, 10, 4
+    N = 2000 * Q
+    fs = N * 1000.0
+    sig = oracle.SignalParams(IF=1.25e6, Fs=fs)
+    spec = SynthSpec(fs=fs, if_hz=1.25e6, samples_per_ms=N, sats=[SatSpec(5, 1234.0, 777, 3.0)])
+    raw = np.frombuffer(synth_if(spec, 0, L + 1), np.int8)
+    xs = raw[0::2].astype(float) + 1j * raw[1::2].astype(float)
+    t = np.arange(1, L * N + 1, dtype=np.float64)
+    chip = np.fmod(np.floor((1.0 / fs * t) / (1.0 / sig.codeFreqBasis)), 1023.0).astype(np.uint16)
+    ca = oracle.generate_ca_code(5).astype(np.int8)
+    cd = 777
+    start = N - cd - 1
+    F = L * N * K
+    s_long = xs[start:start + L * N] * ca[chip]
+    for n2, r in ((0, 0), (3, 1), (9, 3)):
+        out = np.zeros(2 * N, np.float32)
+        rc = emu.emu_fine_unit(Q, R, P(raw), P(chip), P(ca), 2, 1, C.c_float(0), C.c_float(0), start, L, n2, r,
+                               C.c_longlong(F), P(out))
+        assert rc == 0
+        n = L * np.arange(N) + n2
+        want = np.fft.fft(s_long[n] * np.exp(-2j * np.pi * ((n * r) % F) / F))
+        assert np.abs(out.view(np.complex64) - want).max() <= 3e-6 * np.abs(want).max()
