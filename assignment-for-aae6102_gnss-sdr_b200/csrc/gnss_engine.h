@@ -72,7 +72,7 @@ struct Geo {
 
 template <int Q, int R>
 struct Split {
-    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "CTAs per transform");
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "CTAs per transform");
     static constexpr int A = 16 / R;                       // a-rows per CTA
     static constexpr int ROW = Geo<Q>::ROW;                // real columns per a-row
     static constexpr int RS = ROW + (ROW & 1);             // a-row stride in cf: even, so column pairs are 16-B aligned

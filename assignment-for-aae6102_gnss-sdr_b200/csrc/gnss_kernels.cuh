@@ -69,6 +69,16 @@ __device__ __forceinline__ void pass2_all(cf* D, const cf* tw, int tid) {
     if (t < S::P2_TASKS) pass2_task<Q, R>(t, D, tw);
 }
 
+// pass 3 over the CTA.  (A 5-lanes-per-task cooperative form for the few leftover tasks -- P3_TASKS is
+// just above the thread count -- was measured in r01 and LOST 8 %: its address arithmetic raised the
+// register pressure of the surrounding code, which sits at the 128-register limit.  Plain rounds it is.)
+template <int Q, int R, int T>
+__device__ __forceinline__ void pass3_all(cf* D, const cf* tw, int tid) {
+    using S = Split<Q, R>;
+    (void)tw;
+    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+}
+
 struct RedScratch {
     float wv[32];
     int wm[32];
@@ -139,7 +149,7 @@ __device__ __forceinline__ void unit_device(const Loader& ld, Storer& st, cf* D,
     __syncthreads();
     pass2_all<Q, R, T>(D, tw, tid);
     __syncthreads();
-    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+    pass3_all<Q, R, T>(D, tw, tid);
     cl_sync<R>();
     for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
     cl_sync<R>();
@@ -164,7 +174,7 @@ __device__ __forceinline__ void unit_device_pipelined(const Loader& ld, Storer& 
     __syncthreads();
     pass2_all<Q, R, T>(D, tw, tid);
     __syncthreads();
-    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+    pass3_all<Q, R, T>(D, tw, tid);
     cl_sync<R>();
     for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
     cl_arrive<R>();
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
         __syncthreads();
         pass2_all<Q, R, T>(D, tw, tid);
         __syncthreads();
-        for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+        pass3_all<Q, R, T>(D, tw, tid);
         // Software pipeline over the K blocks.  Per iteration: rows of block k leave for L2 (posted
         // stores), passes 1-2 of block k+1 run while they drain and while the other CTAs catch up,
         // then pass 4 of block k reads all 16 rows back from L2, then pass 3 of block k+1.
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
             for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
             if (more) {
                 __syncthreads();
-                for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+                pass3_all<Q, R, T>(D, tw, tid);
             }
         }
         __syncthreads();
@@ -510,7 +520,6 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     unsigned target = 0;                       // arrivals expected so far (R per barrier)
     fill_tw125(tw, tid, T);
     PowerAccumStorer st{acc};
-
     for (int row = group; row < a.P * a.B; row += ngroups) {
         const int p = row % a.P, b = row / a.P;
         for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         __syncthreads();
         pass2_all<Q, R, T>(D, tw, tid);
         __syncthreads();
-        for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+        pass3_all<Q, R, T>(D, tw, tid);
         for (int k = 0; k < a.K; ++k) {
             const bool more = k + 1 < a.K;
             cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
@@ -556,7 +565,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
             if (more) {
                 // pass 2 of block k+1 finished before the barrier above
-                for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
+                pass3_all<Q, R, T>(D, tw, tid);
             }
         }
         __syncthreads();
@@ -655,15 +664,20 @@ static cudaError_t launch_clustered(K kern, const A& args, int units, int R, int
 
 template <int Q, int R, int T, int MINB>
 struct Variant {
+    // K0 / K1 / fine / test transforms always use DSMEM clusters; the portable cluster limit is 8 CTAs, so a
+    // 16-CTA search variant borrows the (8, 256) transform kernels (spectrum layouts do not depend on R).
+    static constexpr int RT = R > 8 ? 8 : R;
+    static constexpr int TT = R > 8 ? 256 : T;
+    static constexpr int MT = R > 8 ? 2 : MINB;
     static cudaError_t prepare() {
         cudaError_t e;
-        e = cudaFuncSetAttribute(code_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        e = cudaFuncSetAttribute(code_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(wipe_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        e = cudaFuncSetAttribute(wipe_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(natural_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        e = cudaFuncSetAttribute(natural_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fine_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::transform);
+        e = cudaFuncSetAttribute(fine_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(search_kernel_coop<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
         if (e != cudaSuccess) return e;
@@ -672,6 +686,7 @@ struct Variant {
         return cudaFuncSetAttribute(search_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
     }
     static cudaError_t launch_search_l2x(const SearchArgs& a, int clusters, cudaStream_t s) {
+        if (R > 8) return cudaErrorInvalidConfiguration;
         return launch_clustered(search_kernel_l2x<Q, R, T, MINB>, a, clusters, R, T, Smem<Q, R>::search, s);
     }
     static cudaError_t launch_search_coop(const SearchArgs& a, int groups, cudaStream_t s) {
@@ -704,22 +719,23 @@ struct Variant {
         return n;
     }
     static cudaError_t launch_code(const CodeArgs& a, int units, cudaStream_t s) {
-        return launch_clustered(code_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+        return launch_clustered(code_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
     static cudaError_t launch_wipe(const WipeArgs& a, int units, cudaStream_t s) {
-        return launch_clustered(wipe_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+        return launch_clustered(wipe_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
     static cudaError_t launch_natural(const NaturalArgs& a, int units, cudaStream_t s) {
-        return launch_clustered(natural_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+        return launch_clustered(natural_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
     static cudaError_t launch_fine(const FineArgs& a, int units, cudaStream_t s) {
-        return launch_clustered(fine_kernel<Q, R, T, MINB>, a, units, R, T, Smem<Q, R>::transform, s);
+        return launch_clustered(fine_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
     static cudaError_t launch_search(const SearchArgs& a, int rows, cudaStream_t s) {
+        if (R > 8) return cudaErrorInvalidConfiguration;       // DSMEM variant needs a portable cluster
         return launch_clustered(search_kernel<Q, R, T, MINB>, a, rows, R, T, Smem<Q, R>::search, s);
     }
     static constexpr VariantOps ops() {
-        return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, R>::transform,
+        return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, RT>::transform,
                           &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_fine, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
                           (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf),

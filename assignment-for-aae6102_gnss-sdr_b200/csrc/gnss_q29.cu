@@ -3,7 +3,8 @@
 namespace gnss {
 const VariantOps* gnss_variants_q29(int* count) {
     static const VariantOps v[] = {
-        Variant<29, 8, 256, 2>::ops(),   // default (first match): fastest measured, profiles/r01
+        Variant<29, 16, 128, 4>::ops(),  // default (first match): fastest measured, profiles/r01
+        Variant<29, 8, 256, 2>::ops(),
         Variant<29, 4, 512, 1>::ops(),
     };
     *count = (int)(sizeof(v) / sizeof(v[0]));

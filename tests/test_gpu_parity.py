@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 # exchange: 1 = DSMEM clusters, 2 = L2 buffer + persistent clusters, 3 = L2 buffer + cooperative CTA groups
 VARIANTS = {6000: [(2, 128, 1), (1, 256, 1), (2, 128, 2), (1, 256, 2), (2, 128, 3), (1, 256, 3)],
             26000: [(2, 512, 1), (4, 256, 1), (4, 512, 1), (2, 512, 2), (4, 256, 2), (2, 512, 3), (4, 256, 3), (8, 128, 3)],
-            58000: [(4, 512, 1), (8, 256, 1), (4, 512, 2), (4, 512, 3), (8, 256, 3)]}
+            58000: [(4, 512, 1), (8, 256, 1), (4, 512, 2), (4, 512, 3), (8, 256, 3), (16, 128, 3)]}
 
 
 def cfg_from(file, signal, acq, prns, **kw):
