@@ -497,6 +497,8 @@ __device__ __forceinline__ void group_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 __device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target) {
+    // acquire polls.  (Relaxed polls + one acquire fence, with and without __nanosleep back-off, were
+    // measured in r01 and were 1-2 % slower: the slower acquire poll is its own back-off.)
     unsigned v;
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -562,11 +564,11 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             }
             if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of block k are in L2
             __syncthreads();
+            // pass 4 of block k and pass 3 of block k+1 share a barrier interval: the L2 latency of the
+            // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
+            // barrier to add slack was measured in r01 and lost 3 %.)
             for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
-            if (more) {
-                // pass 2 of block k+1 finished before the barrier above
-                pass3_all<Q, R, T>(D, tw, tid);
-            }
+            if (more) pass3_all<Q, R, T>(D, tw, tid);
         }
         __syncthreads();
 
