@@ -542,9 +542,20 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
             __syncthreads();                           // pass 3 of block k complete in D
             {
+                // plain coalesced 16-byte stores.  (A TMA bulk copy, cp.async.bulk shared->global with
+                // wait_group before the release, was measured in r01 and was 6 % slower at these sizes.)
                 const float4* src = reinterpret_cast<const float4*>(D);
                 float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
-                for (int i = tid; i < S::D_ELEMS / 2; i += T) dst[i] = src[i];
+                constexpr int NV = S::D_ELEMS / 2, UN = 8;      // 8 loads in flight per thread, then 8 stores
+                int i = tid;
+                for (; i + (UN - 1) * T < NV; i += UN * T) {
+                    float4 v[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) v[u] = src[i + u * T];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) dst[i + u * T] = v[u];
+                }
+                for (; i < NV; i += T) dst[i] = src[i];
             }
             target += R;
             if (more) {
