@@ -302,6 +302,11 @@ def run_gpu(args, cfg):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(cfg["name"])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": cells * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -315,7 +320,8 @@ def run_gpu(args, cfg):
                        "l2": "flushed between steps (256 MiB device memset, outside the per-step event pair)",
                        "latency_ms_32prn": e2e_s / args.steps * 1e3},
             "roofline": {"bound": "fp32", "kernel": "search_kernel", "achieved": achieved, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+                         "traffic_source": "ncu dram bytes per launch, profiles/ncu_traffic.json (not measured in this run)",
                          "peak_source": peak_src, "nominal_peak": 74.4,
                          "algorithmic_flops_per_launch": w_search, "kernel_ms": k2,
                          "wipeoff_fft_kernel_ms": sum(k1_ms) / len(k1_ms),
