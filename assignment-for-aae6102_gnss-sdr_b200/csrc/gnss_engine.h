@@ -81,7 +81,8 @@ struct Split {
     static constexpr int ACC_ELEMS = 16 * CH;              // floats per CTA
     static constexpr int NR = A * Q;                       // (a_local, c') rows of 125 per CTA
     static constexpr int P1_TASKS = A * 125;
-    static constexpr int P2_TASKS = NR * 25;
+    static constexpr int P2_H = (Q + 15) / 16;             // half-warps per (a_local, b2) column of Q rows
+    static constexpr int P2_TASKS = A * 25 * P2_H * 16;    // lane slots (slots with c' >= Q idle)
     static constexpr int P3_TASKS = NR * 5;
     static constexpr int P4_TASKS = CH / 2;                // column PAIRS
 };
@@ -119,21 +120,27 @@ GNSS_HD void pass1_task(int task, int rank, const Loader& ld, cf* __restrict__ D
 }
 
 // ------------------------------------------------------------------ pass 2
-// tw125[j] = exp(-2*pi*i*j/125), j in [0,125).  Task -> (b2 = task / NR, row = task % NR): consecutive
-// lanes walk consecutive rows (stride 125 cf = 13 bank-pairs mod 16: conflict-free) and share b2, so the
-// twiddle reads are broadcasts.
+// tw125[j] = exp(-2*pi*i*j/125), j in [0,125).  Lane slot -> (a_local, b2, c'): the 16 lanes of a half-warp
+// walk 16 consecutive c' of ONE (a_local, b2) column.  Row stride 125 cf = 13 bank-pairs (mod 16), a
+// generator of Z16, so each half-warp touches 16 distinct bank-pairs: conflict-free 64-bit accesses, and
+// the twiddle reads are broadcasts.  Slots with c' >= Q idle (Q = 13: 3 of 16, Q = 29: 3 of 32); the
+// denser mapping that wraps into the next b2 cost 1.4-2.0x the shared-memory wavefronts (ncu r01).
 template <int Q, int R>
-GNSS_HD cf* pass2_ptr(int task, cf* __restrict__ D, int& b2) {
+GNSS_HD cf* pass2_ptr(int slot, cf* __restrict__ D, int& b2) {
     using S = Split<Q, R>;
-    b2 = task / S::NR;
-    const int row = task - b2 * S::NR;
-    const int al = row / Q;
-    return D + row * 125 + al * (S::RS - S::ROW) + b2;
+    const int hw = slot >> 4, l = slot & 15;
+    const int h = hw % S::P2_H, ab = hw / S::P2_H;
+    b2 = ab % 25;
+    const int al = ab / 25;
+    const int c = h * 16 + l;
+    if (c >= Q) return nullptr;
+    return D + al * S::RS + c * 125 + b2;
 }
 template <int Q, int R>
-GNSS_HD void pass2_task(int task, cf* __restrict__ D, const cf* __restrict__ tw125) {
+GNSS_HD void pass2_task(int slot, cf* __restrict__ D, const cf* __restrict__ tw125) {
     int b2;
-    cf* p = pass2_ptr<Q, R>(task, D, b2);
+    cf* p = pass2_ptr<Q, R>(slot, D, b2);
+    if (!p) return;
     cf u[5] = {p[0], p[25], p[50], p[75], p[100]};
     dft_odd<5>(u);
     p[0] = u[0];
@@ -142,12 +149,17 @@ GNSS_HD void pass2_task(int task, cf* __restrict__ D, const cf* __restrict__ tw1
         p[25 * K1] = cmul(u[K1], tw125[b2 * K1]);
     });
 }
-// two tasks at once: all loads, then all math, then all stores (memory-level parallelism)
+// two slots at once: all loads, then all math, then all stores (memory-level parallelism)
 template <int Q, int R>
 GNSS_HD void pass2_task2(int t0, int t1, cf* __restrict__ D, const cf* __restrict__ tw125) {
     int b20, b21;
     cf* p0 = pass2_ptr<Q, R>(t0, D, b20);
     cf* p1 = pass2_ptr<Q, R>(t1, D, b21);
+    if (!p0 || !p1) {                    // same c' for both (t1 - t0 is a multiple of 16): both idle or neither
+        if (p0) pass2_task<Q, R>(t0, D, tw125);
+        if (p1) pass2_task<Q, R>(t1, D, tw125);
+        return;
+    }
     cf u[5] = {p0[0], p0[25], p0[50], p0[75], p0[100]};
     cf v[5] = {p1[0], p1[25], p1[50], p1[75], p1[100]};
     cf wu[5], wv[5];
