@@ -505,6 +505,11 @@ __device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target)
     } while ((int)(v - target) < 0);
 }
 
+#ifdef GNSS_EXPERIMENT_NOBAR   /* timing experiment only (wrong results): total cost of the CTA barriers of the K loop */
+#define GNSS_KSYNC() __syncwarp()
+#else
+#define GNSS_KSYNC() __syncthreads()
+#endif
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     using S = Split<Q, R>;
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         for (int k = 0; k < a.K; ++k) {
             const bool more = k + 1 < a.K;
             cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
-            __syncthreads();                           // pass 3 of block k complete in D
+            GNSS_KSYNC();                           // pass 3 of block k complete in D
             {
                 // plain coalesced 16-byte stores.  (A TMA bulk copy, cp.async.bulk shared->global with
                 // wait_group before the release, was measured in r01 and was 6 % slower at these sizes.)
@@ -563,18 +568,20 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
                 cf z[Q];
                 const bool has = tid < S::P1_TASKS;
                 if (has) pass1_compute<Q, R>(tid, rank, ld, z);
-                __syncthreads();                       // every thread has issued its copy stores
+                GNSS_KSYNC();                       // every thread has issued its copy stores
                 if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier)
                 if (has) pass1_store<Q, R>(tid, z, D);
                 for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
-                __syncthreads();
+                GNSS_KSYNC();
                 pass2_all<Q, R, T>(D, tw, tid);
             } else {
-                __syncthreads();
+                GNSS_KSYNC();
                 if (tid == 0) group_arrive(ctr);
             }
+#ifndef GNSS_EXPERIMENT_NOSPIN   /* timing experiment only (wrong results): how much does group coupling cost? */
             if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of block k are in L2
-            __syncthreads();
+#endif
+            GNSS_KSYNC();
             // pass 4 of block k and pass 3 of block k+1 share a barrier interval: the L2 latency of the
             // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
             // barrier to add slack was measured in r01 and lost 3 %.)
