@@ -225,6 +225,14 @@ struct gnssacq_handle {
     long long* d_sums = nullptr;
     double* d_means = nullptr;
     cf *d_fft_in = nullptr, *d_fft_out = nullptr;
+    // fine-frequency stage scratch, kept between calls (re-made only when L changes)
+    int fine_L = 0;
+    void* d_fine_raw = nullptr;
+    uint16_t* d_fine_chip = nullptr;
+    cf* d_fine_u = nullptr;
+    int8_t* d_fine_ca = nullptr;
+    int* d_fine_start = nullptr;
+    unsigned long long* d_fine_best = nullptr;
     // pinned host
     void* h_if = nullptr;
     gnssacq_result* h_res = nullptr;
@@ -363,6 +371,7 @@ int gnssacq_destroy(gnssacq_handle* h) {
     cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
     cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
+    cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca); cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
     if (h->h_if) cudaFreeHost(h->h_if);
     if (h->h_res) cudaFreeHost(h->h_res);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -639,39 +648,47 @@ int gnssacq_fine_frequency(gnssacq_handle* h, const void* if_long, size_t nbytes
     const long long LN = (long long)L * N, F = LN * K;                          // acquisition.m:108
     if (F > 0xFFFFFFFFll) return fail(h, GNSSACQ_ERR_INVALID_ARG, "fftlength exceeds 2^32");
 
-    void* d_raw = nullptr; uint16_t* d_chip = nullptr; int8_t* d_ca = nullptr; int* d_start = nullptr;
-    cf* d_u = nullptr; unsigned long long* d_best = nullptr;
-    auto cleanup = [&]() { cudaFree(d_raw); cudaFree(d_chip); cudaFree(d_ca); cudaFree(d_start); cudaFree(d_u); cudaFree(d_best); };
+    constexpr int kChunk = 4;                                                   // SVs per pass (scratch ~0.4 GB at N = 58 000)
+    auto cleanup = [&]() {};
 #define CUF(call)                                                                                        \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \
         if (e__ != cudaSuccess) { cleanup(); return fail(h, GNSSACQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
     } while (0)
-    // host tables: chip index of sample t (acquisition.m:104-105, same double arithmetic), C/A chips, start offsets
-    std::vector<uint16_t> chip((size_t)LN);
-    {
+    if (h->fine_L != L) {
+        // (re)build the per-L scratch: chip index of sample t (acquisition.m:104-105, same double arithmetic)
+        cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca);
+        cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
+        h->d_fine_raw = nullptr; h->d_fine_chip = nullptr; h->d_fine_u = nullptr; h->d_fine_ca = nullptr;
+        h->d_fine_start = nullptr; h->d_fine_best = nullptr;
+        h->fine_L = 0;
+        std::vector<uint16_t> chip((size_t)LN);
         const double inv_fs = 1.0 / c.fs_hz, inv_fc = 1.0 / c.code_hz;
         const double codelength = c.code_hz * 1e-3;                             // initParameters.m:47
         for (long long t = 1; t <= LN; ++t) {
             const double idx = std::floor((inv_fs * (double)t) / inv_fc);
             chip[(size_t)(t - 1)] = (uint16_t)std::fmod(idx, codelength);       // rem(.)+1, 0-based here
         }
+        CUF(cudaMalloc(&h->d_fine_raw, need));
+        CUF(cudaMalloc(&h->d_fine_chip, chip.size() * sizeof(uint16_t)));
+        CUF(cudaMalloc(&h->d_fine_ca, (size_t)GNSSACQ_MAX_PRN * 1023));
+        CUF(cudaMalloc(&h->d_fine_start, GNSSACQ_MAX_PRN * sizeof(int)));
+        CUF(cudaMalloc(&h->d_fine_best, GNSSACQ_MAX_PRN * sizeof(unsigned long long)));
+        CUF(cudaMalloc(&h->d_fine_u, (size_t)kChunk * K * L * N * sizeof(cf)));
+        CUF(cudaMemcpy(h->d_fine_chip, chip.data(), chip.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        h->fine_L = L;
     }
+    if (n_sv > GNSSACQ_MAX_PRN) return fail(h, GNSSACQ_ERR_INVALID_ARG, "too many SVs");
+    void* d_raw = h->d_fine_raw; uint16_t* d_chip = h->d_fine_chip; int8_t* d_ca = h->d_fine_ca; int* d_start = h->d_fine_start;
+    cf* d_u = h->d_fine_u; unsigned long long* d_best = h->d_fine_best;
     std::vector<int8_t> ca((size_t)n_sv * 1023);
     std::vector<int> start(n_sv);
     for (int i = 0; i < n_sv; ++i) {
         ca_chips(prn[i], ca.data() + (size_t)i * 1023);
         start[i] = N - code_phase[i] - 1;                                       // acquisition.m:106 (1-based N-codedelay)
     }
-    const int chunk = n_sv < 4 ? n_sv : 4;                                      // SVs per pass (bounds the scratch to ~0.4 GB)
-    CUF(cudaMalloc(&d_raw, need));
-    CUF(cudaMalloc(&d_chip, chip.size() * sizeof(uint16_t)));
-    CUF(cudaMalloc(&d_ca, ca.size()));
-    CUF(cudaMalloc(&d_start, n_sv * sizeof(int)));
-    CUF(cudaMalloc(&d_best, n_sv * sizeof(unsigned long long)));
-    CUF(cudaMalloc(&d_u, (size_t)chunk * K * L * N * sizeof(cf)));
+    const int chunk = n_sv < kChunk ? n_sv : kChunk;
     CUF(cudaMemcpyAsync(d_raw, if_long, need, cudaMemcpyHostToDevice, s));
-    CUF(cudaMemcpyAsync(d_chip, chip.data(), chip.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     CUF(cudaMemcpyAsync(d_ca, ca.data(), ca.size(), cudaMemcpyHostToDevice, s));
     CUF(cudaMemcpyAsync(d_start, start.data(), n_sv * sizeof(int), cudaMemcpyHostToDevice, s));
     CUF(cudaMemsetAsync(d_best, 0, n_sv * sizeof(unsigned long long), s));
@@ -699,7 +716,6 @@ int gnssacq_fine_frequency(gnssacq_handle* h, const void* if_long, size_t nbytes
     CUF(cudaMemcpyAsync(best.data(), d_best, n_sv * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUF(cudaStreamSynchronize(s));
 #undef CUF
-    cleanup();
     for (int i = 0; i < n_sv; ++i) {
         const double idx = (double)(0xFFFFFFFFu - (unsigned)(best[i] & 0xFFFFFFFFull)) + 1.0;   // 1-based FreqPeakIndex (:116)
         double fine = idx * (c.fs_hz / (double)F);                                                // :117
