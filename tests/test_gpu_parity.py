@@ -260,3 +260,21 @@ def test_wrapper_fills_fine_freq():
         if int(sv) in truth:                                      # (a 12 dB threshold also passes the odd noise peak)
             assert abs(ff - signal.IF - truth[int(sv)]) <= 60.0  # 5 Hz bins over a 10 ms window
     gnssacq.release_all()
+
+
+@pytest.mark.parametrize("shape,prns", [("urban", [1, 2, 3, 11, 22, 30]), ("opensky", [3, 5, 16, 26, 29, 32])])
+def test_full_depth_k20_subset_against_oracle(shape, prns):
+    """BASELINE configs 1 and 2 at their real depth (41 bins x 20 non-coherent ms) on a PRN subset (present and
+    absent satellites), row by row against the oracle; and the same rows must come out of the 32-PRN search."""
+    spec = urban_spec() if shape == "urban" else opensky_spec()
+    file, signal, acq = gnssacq.initParameters(shape=shape)
+    raw_b = synth_if(spec, 3, int(acq.datalen))
+    file.dataType, file.dataPrecision = 2, 1
+    ref = oracle_rows(raw_b, file, signal, acq, prns)
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        rows = s.search(raw_b)
+    assert_rows_match(rows, ref, what=f"{shape} K=20")
+    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)))) as s:
+        full = {r.prn: r for r in s.search(raw_b)}
+    for r in rows:                                   # PRN sharding never changes a row (bytes identical)
+        assert bytes(full[r.prn]) == bytes(r)
