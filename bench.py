@@ -58,9 +58,10 @@ def w_fwd(n: int, m: int) -> float:
 
 
 def synth_bytes(cfg) -> bytes:
-    from oracle.synth import opensky_spec, urban_spec, synth_if
-    spec = opensky_spec(seed=6102 + 1) if cfg["shape"] == "opensky" else urban_spec(seed=6102 + 2)
-    return synth_if(spec, 0, cfg["k"] * cfg["m"])
+    """Synthetic IF block of the config (product-side generator: the GPU arm never touches oracle/)."""
+    from gnssacq.synth import opensky_recording, urban_recording
+    rec = opensky_recording(seed=6102 + 1) if cfg["shape"] == "opensky" else urban_recording(seed=6102 + 2)
+    return rec.read(0, cfg["k"] * cfg["m"])
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -141,7 +142,11 @@ def _ref_setup(cfg, kb):
     from oracle.acquisition_ref import carrier_table, samples_from_bytes
     signal = oracle.SignalParams(IF=cfg["if_hz"], Fs=cfg["fs"])
     acq = oracle.AcqParams(freqStep=cfg["fstep"], freqMin=cfg["fmin"], freqNum=cfg["bins"], datalen=kb)
-    raw = samples_from_bytes(synth_bytes(cfg)[: cfg["n"] * 2 * kb * cfg["m"]], 2, 1)
+    # the CPU arm builds its input with the oracle's own generator (byte-identical to the product's, see
+    # tests/test_cabi.py::test_product_and_oracle_generators_agree): nothing of libgnssacq on this path
+    from oracle.synth import opensky_spec, urban_spec, synth_if
+    spec = opensky_spec(seed=6102 + 1) if cfg["shape"] == "opensky" else urban_spec(seed=6102 + 2)
+    raw = samples_from_bytes(synth_if(spec, 0, kb * cfg["m"]), 2, 1)
     _W.update(signal=signal, acq_kb=acq, raw=raw, carrier=carrier_table(signal, acq, 1))
 
 

@@ -2,10 +2,10 @@ import sys, time
 sys.path[:0] = ["/root/repo", "/root/repo/assignment-for-aae6102_gnss-sdr_b200", "/root/repo/tests"]
 import numpy as np, gnssacq
 from gnssacq import api
-from oracle.synth import synth_if, urban_spec, opensky_spec
-for name, spec, fs, if_hz in (("urban", urban_spec(), 26e6, 0.0), ("opensky", opensky_spec(), 58e6, 4.58e6)):
-    raw = synth_if(spec, 0, 20)
-    long_raw = synth_if(spec, 0, 11)
+from gnssacq.synth import urban_recording, opensky_recording
+for name, spec, fs, if_hz in (("urban", urban_recording(), 26e6, 0.0), ("opensky", opensky_recording(), 58e6, 4.58e6)):
+    raw = spec.read(0, 20)
+    long_raw = spec.read(0, 11)
     cfg = gnssacq.make_config(fs_hz=fs, if_hz=if_hz)
     with api.Searcher(cfg) as s:
         rows = s.search(raw)

@@ -111,3 +111,12 @@ def test_mex_gateway_compiles_against_header():
     src = os.path.join(ROOT, "assignment-for-aae6102_gnss-sdr_b200", "matlab", "gnssacq_mex.c")
     subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            "-I", os.path.join(ROOT, "tests", "stubs"), src])
+
+
+def test_product_and_oracle_generators_agree():
+    """gnssacq/synth.py (product side, library C/A tables) and oracle/synth.py (NumPy only) are independent
+    implementations of SURVEY Appendix C: same bytes for the same recording window."""
+    from gnssacq.synth import urban_recording, opensky_recording
+    from oracle.synth import urban_spec, opensky_spec, synth_if
+    assert urban_recording().read(41, 2) == synth_if(urban_spec(), 41, 2)
+    assert opensky_recording(seed=7).read(5, 1) == synth_if(opensky_spec(seed=7), 5, 1)
