@@ -505,7 +505,13 @@ __device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target)
     } while ((int)(v - target) < 0);
 }
 
-#ifdef GNSS_EXPERIMENT_NOBAR   /* timing experiment only (wrong results): total cost of the CTA barriers of the K loop */
+// The software pipeline runs ACROSS row boundaries: passes 1-3 of the next row's first block overlap the
+// exchange of this row's last block (a per-row pipeline idles 0.6 of a block time per row: nothing at
+// K = 20 blocks per row, 10 % at K = 2 -- BASELINE config 5 has 64 032 rows of 2 blocks).
+// Timing-only switches (results invalid by construction, never defined in the product build):
+// GNSS_EXPERIMENT_NOSPIN skips the group barrier wait, GNSS_EXPERIMENT_NOBAR also every CTA barrier of
+// the loop; r01 measured 3.13 / 7.52 ms and 3.01 / 7.55 ms with them: all synchronisation costs 6-9 %.
+#ifdef GNSS_EXPERIMENT_NOBAR
 #define GNSS_KSYNC() __syncwarp()
 #else
 #define GNSS_KSYNC() __syncthreads()
@@ -524,142 +530,141 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     cf* xch = a.scratch + (size_t)group * 2 * 16 * S::RS;
     unsigned* ctr = a.group_ctr + group;
     Candidate* slots = a.row_slots + (size_t)group * R;
-    unsigned target = 0;                       // arrivals expected so far (R per barrier)
+    unsigned target = 0;
     fill_tw125(tw, tid, T);
     PowerAccumStorer st{acc};
-    for (int row = group; row < a.P * a.B; row += ngroups) {
+    const int n_rows = a.P * a.B;
+    auto loader_of = [&](int row) {           // loader of block 0 of a row (two dependent table reads: once per row)
         const int p = row % a.P, b = row / a.P;
-        for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
         int sa, sb, sc;
         G::shift_coords(a.bin_shift[b], sa, sb, sc);
-        const cf* ccp = a.cc + (size_t)p * G::N;
-        const cf* xb = a.x + (size_t)a.bin_base[b] * a.K * G::NX;
+        return SearchLoader{a.cc + (size_t)p * G::N, a.x + (size_t)a.bin_base[b] * a.K * G::NX, sa, sb, sc};
+    };
+    int row = group;
+    if (row >= n_rows) return;
+    int k = 0, par = 0;
+    for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+    SearchLoader ld = loader_of(row);
+    for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+    __syncthreads();
+    pass2_all<Q, R, T>(D, tw, tid);
+    __syncthreads();
+    pass3_all<Q, R, T>(D, tw, tid);
+    for (;;) {
+        const bool last_of_row = (k + 1 == a.K);
+        const int nrow = last_of_row ? row + ngroups : row;
+        const bool more = nrow < n_rows;
+        cf* buf = xch + (size_t)par * 16 * S::RS;
+        par ^= 1;
+        GNSS_KSYNC();                           // pass 3 of the current block complete in D
         {
-            SearchLoader ld{ccp, xb, sa, sb, sc};
-            for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+            // plain coalesced 16-byte stores.  (A TMA bulk copy, cp.async.bulk shared->global with
+            // wait_group before the release, was measured in r01 and was 6 % slower at these sizes.)
+            const float4* src = reinterpret_cast<const float4*>(D);
+            float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
+            for (int i = tid; i < S::D_ELEMS / 2; i += T) dst[i] = src[i];
         }
-        __syncthreads();
-        pass2_all<Q, R, T>(D, tw, tid);
-        __syncthreads();
-        pass3_all<Q, R, T>(D, tw, tid);
-        for (int k = 0; k < a.K; ++k) {
-            const bool more = k + 1 < a.K;
-            cf* buf = xch + (size_t)(k & 1) * 16 * S::RS;
-            GNSS_KSYNC();                           // pass 3 of block k complete in D
-            {
-                // plain coalesced 16-byte stores.  (A TMA bulk copy, cp.async.bulk shared->global with
-                // wait_group before the release, was measured in r01 and was 6 % slower at these sizes.)
-                const float4* src = reinterpret_cast<const float4*>(D);
-                float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
-                constexpr int NV = S::D_ELEMS / 2, UN = 8;      // 8 loads in flight per thread, then 8 stores
-                int i = tid;
-                for (; i + (UN - 1) * T < NV; i += UN * T) {
-                    float4 v[UN];
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) v[u] = src[i + u * T];
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) dst[i + u * T] = v[u];
-                }
-                for (; i < NV; i += T) dst[i] = src[i];
-            }
-            target += R;
-            if (more) {
-                SearchLoader ld{ccp, xb + (size_t)(k + 1) * G::NX, sa, sb, sc};
-                cf z[Q];
-                const bool has = tid < S::P1_TASKS;
-                if (has) pass1_compute<Q, R>(tid, rank, ld, z);
-                GNSS_KSYNC();                       // every thread has issued its copy stores
-                if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier)
-                if (has) pass1_store<Q, R>(tid, z, D);
-                for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
-                GNSS_KSYNC();
-                pass2_all<Q, R, T>(D, tw, tid);
-            } else {
-                GNSS_KSYNC();
-                if (tid == 0) group_arrive(ctr);
-            }
-#ifndef GNSS_EXPERIMENT_NOSPIN   /* timing experiment only (wrong results): how much does group coupling cost? */
-            if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of block k are in L2
-#endif
+        target += R;
+        if (more) {
+            if (last_of_row) ld = loader_of(nrow); else ld.x += G::NX;
+            cf z[Q];
+            const bool has = tid < S::P1_TASKS;
+            if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+            GNSS_KSYNC();                       // every thread has issued its copy stores
+            if (tid == 0) group_arrive(ctr);
+            if (has) pass1_store<Q, R>(tid, z, D);
+            for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
             GNSS_KSYNC();
-            // pass 4 of block k and pass 3 of block k+1 share a barrier interval: the L2 latency of the
-            // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
-            // barrier to add slack was measured in r01 and lost 3 %.)
-            for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
-            if (more) pass3_all<Q, R, T>(D, tw, tid);
+            pass2_all<Q, R, T>(D, tw, tid);
+        } else {
+            GNSS_KSYNC();
+            if (tid == 0) group_arrive(ctr);
         }
-        __syncthreads();
-
-        // ---- K3 through global slots ----
-        float bv = -1.f;
-        int bm = INT_MAX;
-        double ss = 0.0;
-        for (int e = tid; e < S::ACC_ELEMS; e += T) {
-            const int ap = e / S::CH, t = e - ap * S::CH;
-            const int col = rank * S::CH + t;
-            if (col < S::ROW) {
-                const float v = acc[e];
-                const int m = G::lag_of(ap, col);
-                if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
-                ss += (double)v * (double)v;
-                if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
-            }
-        }
-        block_reduce<T>(bv, bm, ss, rs);
-        target += R;
-        if (tid == 0) {
-            Candidate c; c.peak = bv; c.lag = bm; c.sum_all = ss; c.sum_win = 0.0;
-            slots[rank] = c;
-            group_arrive(ctr);
-            group_spin(ctr, target);
-            float gv = -1.f;
-            int gm = INT_MAX;
-            for (int r = 0; r < R; ++r) {
-                const float ov = __ldcg(&slots[r].peak);
-                const int om = __ldcg(&slots[r].lag);
-                if (peak_better(ov, om, gv, gm)) { gv = ov; gm = om; }
-            }
-            rs->g_peak = gv;
-            rs->g_lag = gm;
-        }
-        __syncthreads();
-        const int gm = rs->g_lag;
-        double wsum = 0.0;
-        for (int i = tid; i < 2 * a.w - 1; i += T) {
-            const int m = gm - (a.w - 1) + i;
-            if (m >= 0 && m < G::N) {
-                int ap, col;
-                G::cell_of_lag(m, ap, col);
-                if (col / S::CH == rank) {
-                    const float v = acc[ap * S::CH + (col - rank * S::CH)];
-                    wsum += (double)v * (double)v;
+#ifndef GNSS_EXPERIMENT_NOSPIN
+        if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of this block are in L2
+#endif
+        GNSS_KSYNC();
+        // pass 4 of this block and pass 3 of the next share a barrier interval: the L2 latency of the
+        // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
+        // barrier to add slack was measured in r01 and lost 3 %.)
+        for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
+        if (more) pass3_all<Q, R, T>(D, tw, tid);
+        if (last_of_row) {
+            __syncthreads();                       // accumulator of `row` complete
+            const int p = row % a.P, b = row / a.P;
+            float bv = -1.f;
+            int bm = INT_MAX;
+            double ss = 0.0;
+            for (int e = tid; e < S::ACC_ELEMS; e += T) {
+                const int ap = e / S::CH, t = e - ap * S::CH;
+                const int col = rank * S::CH + t;
+                if (col < S::ROW) {
+                    const float v = acc[e];
+                    const int m = G::lag_of(ap, col);
+                    if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
+                    ss += (double)v * (double)v;
+                    if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
                 }
             }
-        }
-        float dv = -1.f;
-        int dm = INT_MAX;
-        block_reduce<T>(dv, dm, wsum, rs);
-        target += R;
-        if (tid == 0) {
-            slots[rank].sum_win = wsum;
-            group_arrive(ctr);
-            group_spin(ctr, target);
-            if (rank == 0) {
-                double s_all = 0.0, s_win = 0.0;
+            block_reduce<T>(bv, bm, ss, rs);
+            target += R;
+            if (tid == 0) {
+                Candidate c; c.peak = bv; c.lag = bm; c.sum_all = ss; c.sum_win = 0.0;
+                slots[rank] = c;
+                group_arrive(ctr);
+                group_spin(ctr, target);
+                float gv = -1.f;
+                int gm = INT_MAX;
                 for (int r = 0; r < R; ++r) {
-                    s_all += __ldcg(&slots[r].sum_all);
-                    s_win += __ldcg(&slots[r].sum_win);
+                    const float ov = __ldcg(&slots[r].peak);
+                    const int om = __ldcg(&slots[r].lag);
+                    if (peak_better(ov, om, gv, gm)) { gv = ov; gm = om; }
                 }
-                Candidate c;
-                c.peak = rs->g_peak;
-                c.lag = rs->g_lag;
-                c.sum_all = s_all;
-                c.sum_win = s_win;
-                a.cand[(size_t)p * a.B + b] = c;
+                rs->g_peak = gv;
+                rs->g_lag = gm;
             }
+            __syncthreads();
+            const int gm = rs->g_lag;
+            double wsum = 0.0;
+            for (int i = tid; i < 2 * a.w - 1; i += T) {
+                const int m = gm - (a.w - 1) + i;
+                if (m >= 0 && m < G::N) {
+                    int ap, col;
+                    G::cell_of_lag(m, ap, col);
+                    if (col / S::CH == rank) {
+                        const float v = acc[ap * S::CH + (col - rank * S::CH)];
+                        wsum += (double)v * (double)v;
+                    }
+                }
+            }
+            float dv = -1.f;
+            int dm = INT_MAX;
+            block_reduce<T>(dv, dm, wsum, rs);
+            target += R;
+            if (tid == 0) {
+                slots[rank].sum_win = wsum;
+                group_arrive(ctr);
+                group_spin(ctr, target);
+                if (rank == 0) {
+                    double s_all = 0.0, s_win = 0.0;
+                    for (int r = 0; r < R; ++r) {
+                        s_all += __ldcg(&slots[r].sum_all);
+                        s_win += __ldcg(&slots[r].sum_win);
+                    }
+                    Candidate c;
+                    c.peak = rs->g_peak;
+                    c.lag = rs->g_lag;
+                    c.sum_all = s_all;
+                    c.sum_win = s_win;
+                    a.cand[(size_t)p * a.B + b] = c;
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+            // (the next write to acc is pass 4 of the next block, several CTA barriers away)
         }
-        // the slots are rewritten at the end of the next row, K block barriers later: no extra barrier
-        __syncthreads();
+        if (!more) break;
+        if (last_of_row) { row = nrow; k = 0; } else { ++k; }
     }
 }
 
@@ -701,6 +706,7 @@ struct Variant {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(search_kernel_coop<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
         if (e != cudaSuccess) return e;
+
         e = cudaFuncSetAttribute(search_kernel_l2x<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(search_kernel<Q, R, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, R>::search);
