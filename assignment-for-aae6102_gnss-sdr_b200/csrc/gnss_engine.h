@@ -70,6 +70,36 @@ struct Geo {
     }
 };
 
+// Transposed exchange layout ("XT") of the cooperative search kernel: pass 3 leaves its results for pass 4
+// directly in the L2-resident exchange buffer as [16 a][25 k2][NTP] with t = c'*5 + k1 fastest, so that the
+// 25 stores of a pass-3 task are coalesced across the lanes of a warp (no shared-memory write, no copy-out
+// pass) and pass 4 still reads 16-byte pairs.  NTP = 5Q + 1 keeps rows even (pair alignment); column t = 5Q
+// of every k2 row is padding.
+template <int Q>
+struct GeoX {
+    static constexpr int NT = 5 * Q;               // pass-3 tasks per a-row
+    static constexpr int NTP = NT + (NT & 1);      // padded (even)
+    static constexpr int RSX = 25 * NTP;           // cf per a-row of the exchange buffer
+    GNSS_HD static bool valid(int e) { return e < RSX && (e % NTP) < NT; }
+    // lag of (a', e)
+    GNSS_HD static int lag_of(int ap, int e) {
+        const int k2 = e / NTP, t = e - k2 * NTP;
+        const int cp = t / 5, k1 = t - cp * 5;
+        return Geo<Q>::crt(ap, k1 + 5 * k2, cp);
+    }
+    GNSS_HD static void cell_of_lag(int m, int& ap, int& e) {
+        ap = m & 15;
+        const int bp = m % 125;
+        e = (bp / 5) * NTP + (m % Q) * 5 + (bp % 5);
+    }
+};
+template <int Q, int R>
+struct SplitX {
+    static constexpr int CHX = 2 * ((GeoX<Q>::RSX + 2 * R - 1) / (2 * R));   // exchange columns per CTA (even)
+    static constexpr int ACC_ELEMS = 16 * CHX;
+    static constexpr int P4_TASKS = CHX / 2;
+};
+
 template <int Q, int R>
 struct Split {
     static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "CTAs per transform");
@@ -197,6 +227,45 @@ GNSS_HD void pass3_task(int task, cf* __restrict__ D) {
     });
 }
 
+// pass 3, results to the XT exchange buffer instead of back into D.  xrow0 = &buf[a = rank*A][0][0].
+template <int Q, int R>
+GNSS_HD void pass3_task_xt(int task, const cf* __restrict__ D, cf* __restrict__ xrow0) {
+    using S = Split<Q, R>;
+    using X = GeoX<Q>;
+    const int al = task / (5 * Q);
+    const cf* p = D + task * 25 + al * (S::RS - S::ROW);
+    cf v[25];
+    static_for<0, 25>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        v[I] = p[I];
+    });
+    dft25(v);
+    cf* q = xrow0 + al * X::RSX + (task - al * X::NT);        // [al][k2 = 0][t]
+    static_for<0, 25>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;                 // k2 = I
+        q[I * X::NTP] = v[5 * (I % 5) + I / 5];
+    });
+}
+// pass 4 over the XT buffer: task j = exchange columns (e, e+1), e = rank*CHX + 2j
+template <int Q, int R, class Storer>
+GNSS_HD void pass4_task_xt(int j, int rank, const cf* __restrict__ X, Storer& st) {
+    using GX = GeoX<Q>;
+    using SX = SplitX<Q, R>;
+    const int t = 2 * j;
+    const int e = rank * SX::CHX + t;
+    if (t >= SX::CHX || e >= GX::RSX) return;
+    cf w0[16], w1[16];
+    static_for<0, 16>([&](auto ac) {
+        constexpr int Aidx = decltype(ac)::value;
+        const cf2 v = ld_cg2(reinterpret_cast<const cf2*>(X + Aidx * GX::RSX + e));
+        w0[Aidx] = v.lo;
+        w1[Aidx] = v.hi;
+    });
+    dft16(w0);
+    dft16(w1);
+    st.template store2x<Q, R>(t, w0, w1);
+}
+
 // ------------------------------------------------------------------ pass 4
 // Dall[r] = D buffer of cluster CTA r (DSMEM-mapped on the GPU).  One task = two adjacent columns:
 // the 16 rows are fetched with 16-byte loads (half the number of remote requests).
@@ -275,7 +344,20 @@ struct SearchLoader {
 };
 
 struct PowerAccumStorer {
-    float* __restrict__ acc;        // [16][CH] floats of this CTA
+    float* __restrict__ acc;        // [16][CH] (or [16][CHX] in the XT layout) floats of this CTA
+    template <int Q, int R>
+    GNSS_HD void store2x(int t, const cf (&w0)[16], const cf (&w1)[16]) {
+        constexpr int CHX = SplitX<Q, R>::CHX;
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int AP = (I / 4) + 4 * (I % 4);
+            cf* p = reinterpret_cast<cf*>(acc + AP * CHX + t);
+            cf v = *p;
+            v.x += cnorm(w0[I]);
+            v.y += cnorm(w1[I]);
+            *p = v;
+        });
+    }
     template <int Q, int R>
     GNSS_HD void store2(int /*col*/, int t, const cf (&w0)[16], const cf (&w1)[16]) {
         constexpr int CH = Split<Q, R>::CH;

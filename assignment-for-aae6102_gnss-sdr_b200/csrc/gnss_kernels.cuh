@@ -93,7 +93,8 @@ template <int Q, int R>
 struct Smem {
     using S = Split<Q, R>;
     static constexpr size_t d_bytes = (size_t)S::D_ELEMS * sizeof(cf);
-    static constexpr size_t acc_bytes = (size_t)S::ACC_ELEMS * sizeof(float);
+    static constexpr size_t acc_floats = S::ACC_ELEMS > SplitX<Q, R>::ACC_ELEMS ? S::ACC_ELEMS : SplitX<Q, R>::ACC_ELEMS;
+    static constexpr size_t acc_bytes = acc_floats * sizeof(float);
     static constexpr size_t tw_bytes = 125 * sizeof(cf);
     static constexpr size_t red_bytes = ((sizeof(RedScratch) + 15) / 16) * 16;
     static constexpr size_t transform = d_bytes + tw_bytes;
@@ -520,14 +521,17 @@ template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     using S = Split<Q, R>;
     using G = Geo<Q>;
+    using GX = GeoX<Q>;
+    using SX = SplitX<Q, R>;
     const int tid = threadIdx.x;
     const int rank = blockIdx.x % R, group = blockIdx.x / R, ngroups = gridDim.x / R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* D = reinterpret_cast<cf*>(smem_raw);
-    float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
-    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);                 // [16][CHX] (XT layout)
+    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
     RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
-    cf* xch = a.scratch + (size_t)group * 2 * 16 * S::RS;
+    constexpr size_t XBUF = (size_t)16 * GX::RSX;                          // cf per exchange buffer
+    cf* xch = a.scratch + (size_t)group * 2 * XBUF;
     unsigned* ctr = a.group_ctr + group;
     Candidate* slots = a.row_slots + (size_t)group * R;
     unsigned target = 0;
@@ -543,35 +547,30 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     int row = group;
     if (row >= n_rows) return;
     int k = 0, par = 0;
-    for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+    for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
     SearchLoader ld = loader_of(row);
     for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
     __syncthreads();
     pass2_all<Q, R, T>(D, tw, tid);
     __syncthreads();
-    pass3_all<Q, R, T>(D, tw, tid);
+    // pass 3 leaves its results directly in the L2-resident exchange buffer (transposed "XT" layout: the 25
+    // stores of a task are coalesced across the warp) -- no shared-memory write, no copy-out pass
+    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, xch + (size_t)rank * S::A * GX::RSX);
     for (;;) {
         const bool last_of_row = (k + 1 == a.K);
         const int nrow = last_of_row ? row + ngroups : row;
         const bool more = nrow < n_rows;
-        cf* buf = xch + (size_t)par * 16 * S::RS;
+        const cf* buf = xch + (size_t)par * XBUF;          // rows of the current block (all CTAs write into it)
+        cf* nbuf = xch + (size_t)(par ^ 1) * XBUF;         // ... of the next block
         par ^= 1;
-        GNSS_KSYNC();                           // pass 3 of the current block complete in D
-        {
-            // plain coalesced 16-byte stores.  (A TMA bulk copy, cp.async.bulk shared->global with
-            // wait_group before the release, was measured in r01 and was 6 % slower at these sizes.)
-            const float4* src = reinterpret_cast<const float4*>(D);
-            float4* dst = reinterpret_cast<float4*>(buf + (size_t)rank * S::A * S::RS);
-            for (int i = tid; i < S::D_ELEMS / 2; i += T) dst[i] = src[i];
-        }
         target += R;
         if (more) {
             if (last_of_row) ld = loader_of(nrow); else ld.x += G::NX;
             cf z[Q];
             const bool has = tid < S::P1_TASKS;
             if (has) pass1_compute<Q, R>(tid, rank, ld, z);
-            GNSS_KSYNC();                       // every thread has issued its copy stores
-            if (tid == 0) group_arrive(ctr);
+            GNSS_KSYNC();                          // every thread is done with pass 3 of the current block
+            if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier): its rows are in L2
             if (has) pass1_store<Q, R>(tid, z, D);
             for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
             GNSS_KSYNC();
@@ -587,20 +586,21 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         // pass 4 of this block and pass 3 of the next share a barrier interval: the L2 latency of the
         // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
         // barrier to add slack was measured in r01 and lost 3 %.)
-        for (int t = tid; t < S::P4_TASKS; t += T) pass4_task_flat<Q, R>(t, rank, buf, st);
-        if (more) pass3_all<Q, R, T>(D, tw, tid);
+        for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
+        if (more)
+            for (int t = tid; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
         if (last_of_row) {
             __syncthreads();                       // accumulator of `row` complete
             const int p = row % a.P, b = row / a.P;
             float bv = -1.f;
             int bm = INT_MAX;
             double ss = 0.0;
-            for (int e = tid; e < S::ACC_ELEMS; e += T) {
-                const int ap = e / S::CH, t = e - ap * S::CH;
-                const int col = rank * S::CH + t;
-                if (col < S::ROW) {
+            for (int e = tid; e < SX::ACC_ELEMS; e += T) {
+                const int ap = e / SX::CHX, t = e - ap * SX::CHX;
+                const int ex = rank * SX::CHX + t;
+                if (GX::valid(ex)) {
                     const float v = acc[e];
-                    const int m = G::lag_of(ap, col);
+                    const int m = GX::lag_of(ap, ex);
                     if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
                     ss += (double)v * (double)v;
                     if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
@@ -629,10 +629,10 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             for (int i = tid; i < 2 * a.w - 1; i += T) {
                 const int m = gm - (a.w - 1) + i;
                 if (m >= 0 && m < G::N) {
-                    int ap, col;
-                    G::cell_of_lag(m, ap, col);
-                    if (col / S::CH == rank) {
-                        const float v = acc[ap * S::CH + (col - rank * S::CH)];
+                    int ap, ex;
+                    GX::cell_of_lag(m, ap, ex);
+                    if (ex / SX::CHX == rank) {
+                        const float v = acc[ap * SX::CHX + (ex - rank * SX::CHX)];
                         wsum += (double)v * (double)v;
                     }
                 }
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
                 }
             }
             __syncthreads();
-            for (int e = tid; e < S::ACC_ELEMS; e += T) acc[e] = 0.f;
+            for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
             // (the next write to acc is pass 4 of the next block, several CTA barriers away)
         }
         if (!more) break;
@@ -764,7 +764,7 @@ struct Variant {
         return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, RT>::transform,
                           &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_fine, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
-                          (size_t)2 * 16 * Split<Q, R>::RS * sizeof(cf),
+                          (size_t)2 * 16 * (Split<Q, R>::RS > GeoX<Q>::RSX ? Split<Q, R>::RS : GeoX<Q>::RSX) * sizeof(cf),
                           &launch_search_coop, &max_groups_coop};
     }
 };

@@ -124,6 +124,47 @@ static void gx_to_natural(const cf* g, cf* nat) {   // c-extended layout [16][2Q
                 nat[G::good(a, b, c)] = v;
             }
 }
+// search row through the transposed (XT) exchange path of the cooperative kernel
+template <int Q, int R>
+static int search_row_xt(const cf* cc, const cf* x_blocks, int K, int shift, float* acc_by_lag) {
+    using S = Split<Q, R>;
+    using G = Geo<Q>;
+    using GX = GeoX<Q>;
+    using SX = SplitX<Q, R>;
+    std::vector<std::vector<cf>> D(R, std::vector<cf>(S::D_ELEMS));
+    std::vector<std::vector<float>> acc(R, std::vector<float>(SX::ACC_ELEMS, 0.f));
+    std::vector<cf> xbuf((size_t)16 * GX::RSX, mk(1e30f, 1e30f));
+    auto tw = make_tw125();
+    int sa, sb, sc;
+    G::shift_coords(shift, sa, sb, sc);
+    for (int k = 0; k < K; ++k) {
+        SearchLoader ld{cc, x_blocks + (size_t)k * G::NX, sa, sb, sc};
+        for (int r = 0; r < R; ++r) {
+            for (int t = 0; t < S::P1_TASKS; ++t) pass1_task<Q, R>(t, r, ld, D[r].data());
+            for (int t = 0; t < S::P2_TASKS; ++t) pass2_task<Q, R>(t, D[r].data(), tw.data());
+            for (int t = 0; t < S::P3_TASKS; ++t) pass3_task_xt<Q, R>(t, D[r].data(), xbuf.data() + (size_t)r * S::A * GX::RSX);
+        }
+        for (int r = 0; r < R; ++r) {
+            PowerAccumStorer st{acc[r].data()};
+            for (int j = 0; j < SX::P4_TASKS; ++j) pass4_task_xt<Q, R>(j, r, xbuf.data(), st);
+        }
+    }
+    for (int m = 0; m < G::N; ++m) acc_by_lag[m] = -1.f;
+    for (int r = 0; r < R; ++r)
+        for (int ap = 0; ap < 16; ++ap)
+            for (int t = 0; t < SX::CHX; ++t) {
+                const int e = r * SX::CHX + t;
+                if (!GX::valid(e)) continue;
+                acc_by_lag[GX::lag_of(ap, e)] = acc[r][ap * SX::CHX + t];
+            }
+    for (int m = 0; m < G::N; ++m) {
+        int ap, e;
+        GX::cell_of_lag(m, ap, e);
+        if (!GX::valid(e) || GX::lag_of(ap, e) != m) return -1;
+    }
+    return 0;
+}
+
 template <int Q>
 static void g_to_natural(const cf* g, cf* nat) {
     using G = Geo<Q>;
@@ -162,6 +203,10 @@ int emu_gx_to_natural(int Q, const float* g, float* nat) {
     if (Q == 3) { gx_to_natural<3>((const cf*)g, (cf*)nat); return 0; }
     if (Q == 13) { gx_to_natural<13>((const cf*)g, (cf*)nat); return 0; }
     if (Q == 29) { gx_to_natural<29>((const cf*)g, (cf*)nat); return 0; }
+    return -2;
+}
+int emu_search_row_xt(int Q, int R, const float* cc, const float* x_blocks, int K, int shift, float* acc_by_lag) {
+    ALL((search_row_xt<QQ, RR>((const cf*)cc, (const cf*)x_blocks, K, shift, acc_by_lag)))
     return -2;
 }
 int emu_g_to_natural(int Q, const float* g, float* nat) {

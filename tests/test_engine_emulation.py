@@ -72,6 +72,9 @@ def test_engine_passes_against_numpy(emu, Q, R):
             want += np.abs(np.fft.ifft(cfft * np.conj(np.fft.fft(t1)))) ** 2
         assert np.abs(acc - want).max() <= 5e-6 * want.max()
         assert int(acc.argmax()) == int(want.argmax())
+        acc2 = np.zeros(N, np.float32)           # same row through the transposed (XT) exchange path
+        assert emu.emu_search_row_xt(Q, R, P(outg), P(xg), K, s, P(acc2)) == 0
+        assert np.array_equal(acc2, acc)
 
 
 def test_fine_frequency_loader_against_numpy(emu):
