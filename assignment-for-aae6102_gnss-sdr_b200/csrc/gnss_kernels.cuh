@@ -524,6 +524,12 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     using GX = GeoX<Q>;
     using SX = SplitX<Q, R>;
     const int tid = threadIdx.x;
+    // The task counts of passes 2 and 3 are not multiples of the CTA size, so some warp runs one extra
+    // round in each; warp 0 also pays the release fence of the group barrier.  Rotating the thread index
+    // per pass hands the extra rounds to different warps (ncu r01k: warp 0 was the straggler of every phase).
+    // (Per-warp release + arrive right after pass 3 instead of one cumulative release was measured: +1-3 %.)
+    const int tid2 = (tid + T - 32) % T;          // pass 2: last warp first
+    const int tid3 = (tid + T - (64 % T)) % T;    // pass 3: second-to-last warp first
     const int rank = blockIdx.x % R, group = blockIdx.x / R, ngroups = gridDim.x / R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* D = reinterpret_cast<cf*>(smem_raw);
@@ -551,11 +557,11 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     SearchLoader ld = loader_of(row);
     for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
     __syncthreads();
-    pass2_all<Q, R, T>(D, tw, tid);
+    pass2_all<Q, R, T>(D, tw, tid2);
     __syncthreads();
     // pass 3 leaves its results directly in the L2-resident exchange buffer (transposed "XT" layout: the 25
     // stores of a task are coalesced across the warp) -- no shared-memory write, no copy-out pass
-    for (int t = tid; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, xch + (size_t)rank * S::A * GX::RSX);
+    for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, xch + (size_t)rank * S::A * GX::RSX);
     for (;;) {
         const bool last_of_row = (k + 1 == a.K);
         const int nrow = last_of_row ? row + ngroups : row;
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             if (has) pass1_store<Q, R>(tid, z, D);
             for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
             GNSS_KSYNC();
-            pass2_all<Q, R, T>(D, tw, tid);
+            pass2_all<Q, R, T>(D, tw, tid2);
         } else {
             GNSS_KSYNC();
             if (tid == 0) group_arrive(ctr);
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         // barrier to add slack was measured in r01 and lost 3 %.)
         for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
         if (more)
-            for (int t = tid; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
+            for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
         if (last_of_row) {
             __syncthreads();                       // accumulator of `row` complete
             const int p = row % a.P, b = row / a.P;
