@@ -601,15 +601,41 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             float bv = -1.f;
             int bm = INT_MAX;
             double ss = 0.0;
-            for (int e = tid; e < SX::ACC_ELEMS; e += T) {
-                const int ap = e / SX::CHX, t = e - ap * SX::CHX;
-                const int ex = rank * SX::CHX + t;
-                if (GX::valid(ex)) {
-                    const float v = acc[e];
-                    const int m = GX::lag_of(ap, ex);
-                    if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
-                    ss += (double)v * (double)v;
-                    if (a.surface) a.surface[((size_t)p * a.B + b) * G::N + m] = v;
+            if (a.surface) {                       // debug path: every cell's lag is needed anyway
+                for (int e = tid; e < SX::ACC_ELEMS; e += T) {
+                    const int ap = e / SX::CHX, t = e - ap * SX::CHX;
+                    const int ex = rank * SX::CHX + t;
+                    if (GX::valid(ex)) {
+                        const float v = acc[e];
+                        const int m = GX::lag_of(ap, ex);
+                        if (peak_better(v, m, bv, bm)) { bv = v; bm = m; }
+                        ss += (double)v * (double)v;
+                        a.surface[((size_t)p * a.B + b) * G::N + m] = v;
+                    }
+                }
+            } else {
+                // The lag of a cell costs ~40 integer instructions (two divisions, a CRT): only compute it
+                // for cells that can still win.  The padding columns hold exact zeros (their inputs are never
+                // written: the exchange buffer is zero-initialised), so they need no validity test here --
+                // a zero cell only matters when the whole row is zero, and then ties resolve by lag below.
+                const float4* a4 = reinterpret_cast<const float4*>(acc);
+                for (int i = tid; i < SX::ACC_ELEMS / 4; i += T) {
+                    const float4 v = a4[i];
+                    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+                    const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    if (vm >= bv) {                // candidate (ties included): resolve exactly
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = 4 * i + u;
+                            const int ap = e / SX::CHX, t = e - ap * SX::CHX;
+                            const int ex = rank * SX::CHX + t;
+                            if (vv[u] >= bv && GX::valid(ex)) {
+                                const int m = GX::lag_of(ap, ex);
+                                if (peak_better(vv[u], m, bv, bm)) { bv = vv[u]; bm = m; }
+                            }
+                        }
+                    }
                 }
             }
             block_reduce<T>(bv, bm, ss, rs);

@@ -468,6 +468,8 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         }
         if (xmode == 3) h->coop_groups = n; else h->l2x_clusters = n;
         CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
+        // the padding columns of the exchange layout are never written: they must read as exact zeros
+        CUC(cudaMemset(h->d_scratch, 0, (size_t)n * ops->scratch_bytes_per_cluster));
         CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * sizeof(unsigned)));
         CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
