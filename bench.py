@@ -250,8 +250,13 @@ def run_gpu(args, cfg):
     barrier()
     with ClockSampler(local) as clk:
         t_wall0 = time.perf_counter()
+        sync_t = torch.zeros(1, device="cuda")
         for i in range(args.steps):
             flush.zero_()
+            if world > 1:
+                # align the ranks AFTER the flush and BEFORE the timed pair: otherwise another rank's flush
+                # leaks into this rank's step through the broadcast inside it
+                dist.all_reduce(sync_t)
             ev0[i].record()
             shard.enqueue(d)
             ev1[i].record()
