@@ -266,7 +266,7 @@ template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
     GNSS_KERNEL_PROLOGUE
     float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
-    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
     RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
     const int row = unit;                       // row = bin * P + prn_index (PRN fastest: rows in
     const int p = row % a.P, b = row / a.P;     // flight share the same forward spectra in L2)
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
     GNSS_KERNEL_PROLOGUE
     (void)Dall;
     float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
-    cf* tw = reinterpret_cast<cf*>(acc + S::ACC_ELEMS);
+    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
     RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
     const int ncl = gridDim.x / R, slot = unit;
     cf* xch = a.scratch + (size_t)slot * 2 * 16 * S::RS;
@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             GNSS_KSYNC();                          // every thread is done with pass 3 of the current block
             if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier): its rows are in L2
             if (has) pass1_store<Q, R>(tid, z, D);
-            for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+            if constexpr (S::P1_TASKS > T)
+                for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
             GNSS_KSYNC();
             pass2_all<Q, R, T>(D, tw, tid2);
         } else {
