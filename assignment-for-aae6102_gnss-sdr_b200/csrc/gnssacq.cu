@@ -622,6 +622,29 @@ int gnssacq_search(gnssacq_handle* h, const void* if_samples, size_t nbytes, gns
     return gnssacq_fetch_results(h, out, st);
 }
 
+int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n, const void* if_samples, size_t nbytes, gnssacq_result* out) {
+    if (!hs || n < 1 || !if_samples || !out) return GNSSACQ_ERR_INVALID_ARG;
+    for (int i = 0; i < n; ++i) {
+        gnssacq_handle* h = hs[i];
+        if (!h) return GNSSACQ_ERR_INVALID_ARG;
+        if (nbytes < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "IF block shorter than noncoh_blocks*coh_ms ms");
+        CU(cudaSetDevice(h->device));
+        std::memcpy(h->h_if, if_samples, h->if_bytes);
+        CU(cudaEventRecord(h->ev[0], h->stream));
+        CU(cudaMemcpyAsync(h->d_if, h->h_if, h->if_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->have_h2d = true;
+        int rc = enqueue(h, h->d_if);
+        if (rc != GNSSACQ_OK) return rc;
+    }
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = gnssacq_fetch_results(hs[i], out + off, nullptr);
+        if (rc != GNSSACQ_OK) return rc;
+        off += (size_t)hs[i]->P;
+    }
+    return GNSSACQ_OK;
+}
+
 int gnssacq_read_surface(gnssacq_handle* h, int32_t prn_index, float* out) {
     if (!h || !out || prn_index < 0 || prn_index >= h->P) return fail(h, GNSSACQ_ERR_INVALID_ARG, "bad argument");
     if (!h->d_surface) return fail(h, GNSSACQ_ERR_STATE, "handle was created without keep_surface");

@@ -73,6 +73,7 @@ EXPORTS = (
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
+    "gnssacq_search_multi",
 )
 
 
@@ -102,6 +103,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_read_surface.argtypes = [vp, C.c_int32, vp]
     lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
     lib.gnssacq_fine_frequency.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32, vp, vp, vp]
+    lib.gnssacq_search_multi.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_size_t, C.POINTER(Result)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
@@ -158,6 +160,19 @@ def code_replica(cfg: Config, prn: int) -> np.ndarray:
     if rc:
         raise GnssAcqError(rc, STATUS.get(rc, "?"))
     return out
+
+
+def search_multi(searchers: Sequence["Searcher"], if_bytes) -> List[Result]:
+    """One process, several GPUs: every Searcher owns a PRN shard on its own device (cfg.device)."""
+    buf = np.frombuffer(if_bytes, dtype=np.uint8) if not isinstance(if_bytes, np.ndarray) else if_bytes
+    buf = np.ascontiguousarray(buf)
+    hs = (C.c_void_p * len(searchers))(*[s._h for s in searchers])
+    n_rows = sum(s.cfg.n_prn for s in searchers)
+    out = (Result * n_rows)()
+    rc = lib.gnssacq_search_multi(hs, len(searchers), buf.ctypes.data, buf.nbytes, out)
+    if rc:
+        raise GnssAcqError(rc, STATUS.get(rc, "?"))
+    return list(out)
 
 
 def fp32_peak_tflops(device: int = -1) -> float:

@@ -138,6 +138,14 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
  * all-gather that assembles the per-rank PRN shards.  Stream-ordered; no host synchronisation. */
 int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if_samples, size_t nbytes, void* d_out_rows);
 
+/* Single-process multi-GPU convenience (e.g. for the MEX gateway, which lives in one MATLAB process):
+ * `hs[i]` are handles created on different devices (cfg.device) for disjoint PRN shards (cfg.prn[]); the IF
+ * block is staged and copied to every device over its own PCIe link, all shards are enqueued, then fetched.
+ * Rows land in out[] in handle order (sum of the handles' n_prn).  The one-process-per-GPU path
+ * (gnssacq/dist.py: NCCL broadcast + all-gather over NVLink) is the one the benchmark uses. */
+int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n_handles, const void* if_samples, size_t nbytes,
+                         gnssacq_result* out);
+
 /* Fine-frequency stage (replaces acquisition.m:89-121).  `if_long` is the (L+1) ms block
  * acquisition.m:91/96 reads from the same file offset (host memory); for each of the n_sv acquired SVs
  * (prn[i], code_phase[i] = Acquired.codedelay) the code-stripped L ms are zero-padded to

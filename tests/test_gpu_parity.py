@@ -278,3 +278,23 @@ def test_full_depth_k20_subset_against_oracle(shape, prns):
         full = {r.prn: r for r in s.search(raw_b)}
     for r in rows:                                   # PRN sharding never changes a row (bytes identical)
         assert bytes(full[r.prn]) == bytes(r)
+
+
+def test_single_process_multi_handle_search():
+    """gnssacq_search_multi: PRN shards on several handles (several GPUs when visible, else the same one) in ONE
+    process give the bytes of the single-handle table."""
+    import torch
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    raw_b = synth_if(small_spec(fs, if_hz, int(signal.Sample)), 0, 2)
+    prns = list(range(1, 13))
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        full = [bytes(r) for r in s.search(raw_b)]
+    ndev = torch.cuda.device_count()
+    parts = [api.Searcher(cfg_from(file, signal, acq, prns[i * 4:(i + 1) * 4], device=i % ndev)) for i in range(3)]
+    try:
+        rows = api.search_multi(parts, raw_b)
+    finally:
+        for p in parts:
+            p.close()
+    assert [bytes(r) for r in rows] == full
