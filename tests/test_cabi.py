@@ -120,3 +120,14 @@ def test_product_and_oracle_generators_agree():
     from oracle.synth import urban_spec, opensky_spec, synth_if
     assert urban_recording().read(41, 2) == synth_if(urban_spec(), 41, 2)
     assert opensky_recording(seed=7).read(5, 1) == synth_if(opensky_spec(seed=7), 5, 1)
+
+
+def test_c_example_links_against_the_library(tmp_path):
+    """examples/acquire.c uses the ABI from plain C (no Python, no torch): it must compile and link."""
+    import subprocess
+    pkg = os.path.join(ROOT, "assignment-for-aae6102_gnss-sdr_b200", "gnssacq")
+    exe = str(tmp_path / "acquire")
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "acquire.c"), "-L", pkg, "-lgnssacq", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=pkg))
+    assert r.returncode == 2 and "usage" in r.stderr
