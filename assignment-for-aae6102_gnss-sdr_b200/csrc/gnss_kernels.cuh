@@ -550,11 +550,40 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         G::shift_coords(a.bin_shift[b], sa, sb, sc);
         return SearchLoader{a.cc + (size_t)p * G::N, a.x + (size_t)a.bin_base[b] * a.K * G::NX, sa, sb, sc};
     };
-    int row = group;
-    if (row >= n_rows) return;
-    int k = 0, par = 0;
+    // Schedule.  floor(n_rows / ngroups) full rounds of whole rows, strided (row = round*ngroups + group: at
+    // any time the groups work on neighbouring rows, i.e. on the same forward spectra -- contiguous row ranges
+    // per group were measured 7 % slower at Q = 29).  The n_tail remaining rows are dealt out in units of one
+    // block of one row, as contiguous ranges [tb(g), tb(g+1)) of u = tail_row*K + k, so every group gets the
+    // same amount of the tail.  A tail row cut by a range boundary is finished by the group holding its first
+    // block; the groups holding its later parts leave their partial accumulators in HBM and arrive on a counter
+    // of the finishing group.  Those groups never wait for anything, so nobody waits on a waiter.  With
+    // row_granular the tail is dealt out as whole rows too (sums then do not depend on the group count).
+    const int full = n_rows / ngroups, tail_base = full * ngroups, n_tail = n_rows - tail_base;
+    auto tb = [&](int g) -> int {                  // 32-bit on purpose (a 64-bit division here costs the Q = 29 kernel
+                                                   // 14 spilled registers); the host checks ngroups^2 * K < 2^32
+        return a.row_granular ? (g < n_tail ? g : n_tail) * a.K : (int)((unsigned)g * (unsigned)(n_tail * a.K) / (unsigned)ngroups);
+    };
+    // The group's work as a list of row parts {row, first block, end block}: `full` whole rows, then the tail
+    // range cut at its row boundary (it is at most K units long, so it touches at most two rows).  The loop
+    // only carries the part index and the block counter; a part is looked up when it begins and when it ends.
+    struct Part { int row, kb, ke; };
+    auto part = [&](int i) -> Part {
+        if (i < full) return Part{i * ngroups + group, 0, a.K};
+        const int t0 = tb(group), t1 = tb(group + 1), r0 = t0 / a.K, e0 = min(t1, (r0 + 1) * a.K);
+        if (i == full) return Part{tail_base + r0, t0 - r0 * a.K, e0 - r0 * a.K};
+        return Part{tail_base + r0 + 1, 0, t1 - e0};
+    };
+    auto count_parts = [&]() -> int {
+        const int t0 = tb(group), t1 = tb(group + 1);
+        return full + (t0 < t1 ? 1 + (min(t1, (t0 / a.K + 1) * a.K) < t1) : 0);
+    };
+    if (count_parts() == 0) return;
+    int i = 0, par = 0;
+    const Part first = part(0);
+    int left = first.ke - first.kb;                // blocks of part i still to do, this one included
     for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
-    SearchLoader ld = loader_of(row);
+    SearchLoader ld = loader_of(first.row);
+    ld.x += (size_t)first.kb * G::NX;
     for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
     __syncthreads();
     pass2_all<Q, R, T>(D, tw, tid2);
@@ -563,15 +592,20 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     // stores of a task are coalesced across the warp) -- no shared-memory write, no copy-out pass
     for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, xch + (size_t)rank * S::A * GX::RSX);
     for (;;) {
-        const bool last_of_row = (k + 1 == a.K);
-        const int nrow = last_of_row ? row + ngroups : row;
-        const bool more = nrow < n_rows;
+        const bool last_of_part = (left == 1);
+        const bool more = !last_of_part || i + 1 < count_parts();
         const cf* buf = xch + (size_t)par * XBUF;          // rows of the current block (all CTAs write into it)
         cf* nbuf = xch + (size_t)(par ^ 1) * XBUF;         // ... of the next block
         par ^= 1;
         target += R;
         if (more) {
-            if (last_of_row) ld = loader_of(nrow); else ld.x += G::NX;
+            if (last_of_part) {
+                const Part np = part(i + 1);
+                ld = loader_of(np.row);
+                ld.x += (size_t)np.kb * G::NX;
+            } else {
+                ld.x += G::NX;
+            }
             cf z[Q];
             const bool has = tid < S::P1_TASKS;
             if (has) pass1_compute<Q, R>(tid, rank, ld, z);
@@ -596,8 +630,45 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
         if (more)
             for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
-        if (last_of_row) {
-            __syncthreads();                       // accumulator of `row` complete
+        const Part cp = last_of_part ? part(i) : Part{0, 0, 0};
+        const int row = cp.row;
+        if (last_of_part && cp.kb > 0) {
+            // a later part of a row some earlier group finishes: hand the partial accumulator over
+            __syncthreads();
+            float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)group * R + rank) * SX::ACC_ELEMS);
+            float4* a4 = reinterpret_cast<float4*>(acc);
+            for (int q = tid; q < SX::ACC_ELEMS / 4; q += T) {
+                __stcg(dst + q, a4[q]);
+                a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int gf = group - 1;                // the finisher: last group whose range starts at or before the row's
+                while (tb(gf) > (row - tail_base) * a.K) --gf;
+                group_arrive(a.part_ctr + (size_t)gf * R + rank);      // release, cumulative over the CTA barrier
+            }
+        } else if (last_of_part) {
+            __syncthreads();                       // this group's blocks of `row` are in the accumulator
+            if (cp.ke < a.K) {
+                // the remaining blocks were done by the following groups: add their parts, in block order
+                const int row_end = (row - tail_base + 1) * a.K;
+                int parts = 0, g_end = group + 1;  // (a group's range is empty when there are fewer units than groups)
+                for (; g_end < ngroups && tb(g_end) < row_end; ++g_end) parts += tb(g_end + 1) > tb(g_end);
+                if (tid == 0) group_spin(a.part_ctr + (size_t)group * R + rank, (unsigned)parts);
+                __syncthreads();
+                float4* a4 = reinterpret_cast<float4*>(acc);
+                for (int g2 = group + 1; g2 < g_end; ++g2) {
+                    if (tb(g2 + 1) <= tb(g2)) continue;
+                    const float4* src = reinterpret_cast<const float4*>(a.partial + ((size_t)g2 * R + rank) * SX::ACC_ELEMS);
+                    for (int q = tid; q < SX::ACC_ELEMS / 4; q += T) {
+                        const float4 o = __ldcg(src + q);
+                        float4 v = a4[q];
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        a4[q] = v;
+                    }
+                }
+                __syncthreads();
+            }
             const int p = row % a.P, b = row / a.P;
             float bv = -1.f;
             int bm = INT_MAX;
@@ -620,15 +691,15 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
                 // written: the exchange buffer is zero-initialised), so they need no validity test here --
                 // a zero cell only matters when the whole row is zero, and then ties resolve by lag below.
                 const float4* a4 = reinterpret_cast<const float4*>(acc);
-                for (int i = tid; i < SX::ACC_ELEMS / 4; i += T) {
-                    const float4 v = a4[i];
+                for (int q = tid; q < SX::ACC_ELEMS / 4; q += T) {
+                    const float4 v = a4[q];
                     ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
                     const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
                     if (vm >= bv) {                // candidate (ties included): resolve exactly
                         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int e = 4 * i + u;
+                            const int e = 4 * q + u;
                             const int ap = e / SX::CHX, t = e - ap * SX::CHX;
                             const int ex = rank * SX::CHX + t;
                             if (vv[u] >= bv && GX::valid(ex)) {
@@ -697,7 +768,12 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             // (the next write to acc is pass 4 of the next block, several CTA barriers away)
         }
         if (!more) break;
-        if (last_of_row) { row = nrow; k = 0; } else { ++k; }
+        if (last_of_part) {
+            const Part np = part(++i);
+            left = np.ke - np.kb;
+        } else {
+            --left;
+        }
     }
 }
 
@@ -798,7 +874,8 @@ struct Variant {
                           &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_fine, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
                           (size_t)2 * 16 * (Split<Q, R>::RS > GeoX<Q>::RSX ? Split<Q, R>::RS : GeoX<Q>::RSX) * sizeof(cf),
-                          &launch_search_coop, &max_groups_coop};
+                          &launch_search_coop, &max_groups_coop,
+                          (size_t)R * SplitX<Q, R>::ACC_ELEMS * sizeof(float)};
     }
 };
 

@@ -222,6 +222,7 @@ struct gnssacq_handle {
     int coop_groups = 0;           // > 0: use the cluster-free cooperative kernel with this many CTA groups
     unsigned* d_group_ctr = nullptr;
     Candidate* d_row_slots = nullptr;
+    float* d_partial = nullptr;    // cooperative kernel: accumulators of row parts handed between groups
     long long* d_sums = nullptr;
     double* d_means = nullptr;
     cf *d_fft_in = nullptr, *d_fft_out = nullptr;
@@ -307,6 +308,7 @@ int validate(const gnssacq_config* c, std::string& why) {
     if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
     for (int i = 0; i < c->n_prn; ++i)
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->work_split < 0 || c->work_split > 1) { why = "work_split must be 0 (blocks) or 1 (whole rows)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->exchange < 0 || c->exchange > 3) { why = "exchange must be 0 (auto), 1 (DSMEM), 2 (L2 + clusters) or 3 (L2 + cooperative groups)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
         why = "samples_per_ms must be 2000*Q (built: Q = 3, 13, 29 -> 6000, 26000, 58000)";
@@ -369,7 +371,7 @@ int gnssacq_destroy(gnssacq_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
     cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
-    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_partial); cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca); cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
     if (h->h_if) cudaFreeHost(h->h_if);
@@ -461,7 +463,11 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     const int xmode = cfg->exchange ? cfg->exchange : (Q >= 13 ? 3 : 1);
     if (xmode == 2 || xmode == 3) {
         int n = xmode == 3 ? ops->max_groups_coop() : ops->max_clusters_l2x();
-        if (n > h->P * h->B) n = h->P * h->B;
+        // the cooperative kernel deals out single blocks of a row (work_split 0) or whole rows (1); the
+        // clustered one whole rows
+        const bool by_blocks = xmode == 3 && !cfg->work_split && (unsigned long long)n * n * h->K < (1ull << 32);
+        const long long max_useful = by_blocks ? (long long)h->P * h->B * h->K : (long long)h->P * h->B;
+        if (n > max_useful) n = (int)max_useful;
         if (n <= 0) {
             gnssacq_destroy(h);
             return fail(nullptr, GNSSACQ_ERR_CUDA, "persistent search kernel cannot be made resident on this device");
@@ -470,7 +476,8 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
         // the padding columns of the exchange layout are never written: they must read as exact zeros
         CUC(cudaMemset(h->d_scratch, 0, (size_t)n * ops->scratch_bytes_per_cluster));
-        CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * sizeof(unsigned)));
+        CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * (1 + ops->R) * sizeof(unsigned)));     // group barriers + hand-over counters
+        if (by_blocks) CUC(cudaMalloc(&h->d_partial, (size_t)n * ops->partial_bytes_per_group));
         CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
     if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
@@ -541,8 +548,13 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.scratch = h->d_scratch;
     sa.group_ctr = h->d_group_ctr;
     sa.row_slots = h->d_row_slots;
+    sa.partial = h->d_partial;
+    sa.part_ctr = h->d_group_ctr ? h->d_group_ctr + h->coop_groups : nullptr;
+    // (the kernel's unit arithmetic is 32-bit: groups^2 * K must stay below 2^32, else deal out whole rows)
+    sa.row_granular = (h->cfg.work_split || !h->d_partial ||
+                       (unsigned long long)h->coop_groups * h->coop_groups * h->K >= (1ull << 32)) ? 1 : 0;
     if (h->coop_groups > 0) {
-        CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * sizeof(unsigned), s));
+        CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * (1 + h->ops->R) * sizeof(unsigned), s));
         CU(h->ops->launch_search_coop(sa, h->coop_groups, s));
     } else if (h->l2x_clusters > 0) {
         CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));

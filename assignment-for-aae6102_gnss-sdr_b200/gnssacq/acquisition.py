@@ -22,7 +22,8 @@ _searchers: Dict[tuple, api.Searcher] = {}
 
 def config_from_structs(file, signal, acq, *, coh_ms: int = 1, prns: Sequence[int] = tuple(range(1, 33)),
                         snr_threshold_db: float = 12.0, device: int = -1, cluster_ctas: int = 0,
-                        threads: int = 0, keep_surface: bool = False, exchange: int = 0) -> api.Config:
+                        threads: int = 0, keep_surface: bool = False, exchange: int = 0,
+                        work_split: int = 0) -> api.Config:
     """Map exactly the fields acquisition.m reads onto ``gnssacq_config``."""
     return api.make_config(
         fs_hz=float(signal.Fs), if_hz=float(signal.IF), code_hz=float(signal.codeFreqBasis),
@@ -30,7 +31,7 @@ def config_from_structs(file, signal, acq, *, coh_ms: int = 1, prns: Sequence[in
         data_precision=int(file.dataPrecision), freq_min_hz=float(acq.freqMin),
         freq_step_hz=float(acq.freqStep), freq_num=int(acq.freqNum), noncoh_blocks=int(acq.datalen),
         coh_ms=coh_ms, prns=prns, snr_threshold_db=snr_threshold_db, device=device,
-        cluster_ctas=cluster_ctas, threads=threads, keep_surface=keep_surface, exchange=exchange)
+        cluster_ctas=cluster_ctas, threads=threads, keep_surface=keep_surface, exchange=exchange, work_split=work_split)
 
 
 def _key(cfg: api.Config) -> tuple:

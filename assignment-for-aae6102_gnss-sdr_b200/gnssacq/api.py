@@ -41,7 +41,7 @@ class Config(C.Structure):
         ("n_prn", C.c_int32), ("prn", C.c_int32 * GNSSACQ_MAX_PRN),
         ("snr_threshold_db", C.c_double),
         ("device", C.c_int32), ("cluster_ctas", C.c_int32), ("threads", C.c_int32),
-        ("keep_surface", C.c_int32), ("exchange", C.c_int32),
+        ("keep_surface", C.c_int32), ("exchange", C.c_int32), ("work_split", C.c_int32),
     ]
 
 
@@ -125,7 +125,7 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
                 data_type=2, data_precision=1, freq_min_hz=-10000.0, freq_step_hz=500.0,
                 freq_num: Optional[int] = None, noncoh_blocks=20, coh_ms=1,
                 prns: Sequence[int] = tuple(range(1, 33)), snr_threshold_db=12.0, device=-1,
-                cluster_ctas=0, threads=0, keep_surface=False, exchange=0) -> Config:
+                cluster_ctas=0, threads=0, keep_surface=False, exchange=0, work_split=0) -> Config:
     cfg = default_config()
     cfg.fs_hz, cfg.if_hz, cfg.code_hz = fs_hz, if_hz, code_hz
     cfg.samples_per_ms = int(samples_per_ms if samples_per_ms else np.ceil(fs_hz * 1e-3))
@@ -143,6 +143,7 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
     cfg.device, cfg.cluster_ctas, cfg.threads = device, cluster_ctas, threads
     cfg.keep_surface = int(bool(keep_surface))
     cfg.exchange = int(exchange)
+    cfg.work_split = int(work_split)
     return cfg
 
 

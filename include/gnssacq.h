@@ -64,6 +64,11 @@ typedef struct gnssacq_config {
                                  pass.  0 = auto, 1 = distributed shared memory (clusters), 2 = L2-resident
                                  buffer (persistent clusters), 3 = L2-resident buffer, cooperative CTA
                                  groups without clusters (uses every SM) */
+    int32_t work_split;       /* exchange 3 only: how the (PRN, bin) rows are dealt out to the resident CTA groups.
+                                 0 = block-granular (default): a row's noncoh_blocks may be shared by consecutive
+                                 groups whose partial sums are added in block order -- every group gets the same
+                                 work, but the last bits of peak/SNR depend on how many rows the handle has;
+                                 1 = whole rows: a PRN's result is bit-identical whatever shard it is part of */
 } gnssacq_config;
 
 /* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */

@@ -1,0 +1,49 @@
+"""Same-box A/B of two builds of libgnssacq.so (boxes differ by several per cent, so only same-run numbers
+compare).  Usage: python profiles/ab_libs.py name=path/to/lib.so name2=path2 [--prns 4,32] [--rounds 3]"""
+import os
+import subprocess
+import sys
+
+CHILD = r'''
+import sys
+sys.path[:0] = ["/root/repo", "/root/repo/assignment-for-aae6102_gnss-sdr_b200"]
+import gnssacq
+from gnssacq import api
+from gnssacq.synth import urban_recording, opensky_recording
+prns = [int(x) for x in sys.argv[1].split(",")]
+for which in ("urban", "opensky"):
+    spec, fs, if_hz = (urban_recording(), 26e6, 0.0) if which == "urban" else (opensky_recording(), 58e6, 4.58e6)
+    raw = spec.read(0, 20)
+    for n in prns:
+        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1))) as s:
+            best = 1e9
+            for _ in range(8):
+                s.search(raw)
+                best = min(best, s.last_stats.search_ms)
+        print(which, n, round(best, 4), flush=True)
+'''
+
+libs = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and not a.startswith("--")]
+prns = "4,32"
+rounds = 3
+for i, a in enumerate(sys.argv):
+    if a == "--prns":
+        prns = sys.argv[i + 1]
+    if a == "--rounds":
+        rounds = int(sys.argv[i + 1])
+best = {}
+for r in range(rounds):
+    for name, path in libs:
+        env = dict(os.environ, GNSSACQ_LIB=os.path.abspath(path))
+        out = subprocess.run([sys.executable, "-c", CHILD, prns], env=env, capture_output=True, text=True)
+        if out.returncode:
+            print(name, "FAILED", out.stderr[-500:])
+            continue
+        for line in out.stdout.split("\n"):
+            if line.strip():
+                which, n, ms = line.split()
+                key = (which, int(n), name)
+                best[key] = min(best.get(key, 1e9), float(ms))
+for which in ("urban", "opensky"):
+    for n in [int(x) for x in prns.split(",")]:
+        print(which, "prns", n, {name: best.get((which, n, name)) for name, _ in libs}, flush=True)

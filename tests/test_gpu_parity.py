@@ -274,10 +274,53 @@ def test_full_depth_k20_subset_against_oracle(shape, prns):
     with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
         rows = s.search(raw_b)
     assert_rows_match(rows, ref, what=f"{shape} K=20")
-    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)))) as s:
+    # work_split=1 deals out whole rows: PRN sharding then never changes a row (bytes identical)
+    with api.Searcher(cfg_from(file, signal, acq, prns, work_split=1)) as s:
+        rows1 = s.search(raw_b)
+    assert_rows_match(rows1, ref, what=f"{shape} K=20 whole rows")
+    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)), work_split=1)) as s:
         full = {r.prn: r for r in s.search(raw_b)}
-    for r in rows:                                   # PRN sharding never changes a row (bytes identical)
+    for r in rows1:
         assert bytes(full[r.prn]) == bytes(r)
+    # the default block-granular split only changes the order of the K additions per cell
+    for r, r1 in zip(rows, rows1):
+        assert (r.prn, r.code_phase, r.doppler_bin, r.acquired) == (r1.prn, r1.code_phase, r1.doppler_bin, r1.acquired)
+        assert r.peak == pytest.approx(r1.peak, rel=2e-6) and r.snr_db == pytest.approx(r1.snr_db, rel=2e-6)
+
+
+@pytest.mark.parametrize("n,variant,datalen,prns", [
+    (6000, (2, 128, 3), 3, [7]), (6000, (1, 256, 3), 7, [1, 2, 3, 4, 5]),
+    (26000, (8, 128, 3), 20, [1]), (26000, (8, 128, 3), 6, [1, 2, 3, 11]), (26000, (4, 256, 3), 7, [3, 30]),
+    (26000, (8, 128, 3), 1, [1, 2, 3]),
+    (58000, (16, 128, 3), 9, [16]), (58000, (16, 128, 3), 3, [3, 5, 16, 26]), (58000, (8, 256, 3), 2, [16, 32]),
+])
+def test_block_granular_split_of_few_rows(n, variant, datalen, prns):
+    """Few rows on many resident CTA groups (one rank's shard at 8 GPUs, a single-PRN re-acquisition): the
+    cooperative kernel cuts rows at block granularity and the finishing group adds the handed-over partial
+    accumulators.  Rows against the oracle, and against the whole-row schedule of the same kernel."""
+    if n == 6000:
+        fs, if_hz = 6e6, 1.25e6
+        file, signal, acq = structs(fs, if_hz, datalen=datalen)
+        raw_b = synth_if(small_spec(fs, if_hz, n), 0, datalen)
+    else:
+        shape = "urban" if n == 26000 else "opensky"
+        file, signal, acq = gnssacq.initParameters(shape=shape)
+        acq.datalen = datalen
+        raw_b = synth_if(urban_spec() if shape == "urban" else opensky_spec(), 3, datalen)
+        file.dataType, file.dataPrecision = 2, 1
+    ref = oracle_rows(raw_b, file, signal, acq, prns)
+    kw = dict(cluster_ctas=variant[0], threads=variant[1], exchange=variant[2])
+    with api.Searcher(cfg_from(file, signal, acq, prns, **kw)) as s:
+        rows = s.search(raw_b)
+        again = s.search(raw_b)
+        groups = s.last_stats.resident_clusters
+    assert [bytes(r) for r in rows] == [bytes(r) for r in again]          # deterministic
+    assert_rows_match(rows, ref, what=f"N={n} {variant} K={datalen} {len(prns)} PRN on {groups} groups")
+    with api.Searcher(cfg_from(file, signal, acq, prns, work_split=1, **kw)) as s:
+        rows1 = s.search(raw_b)
+    for r, r1 in zip(rows, rows1):
+        assert (r.prn, r.code_phase, r.doppler_bin, r.acquired) == (r1.prn, r1.code_phase, r1.doppler_bin, r1.acquired)
+        assert r.peak == pytest.approx(r1.peak, rel=2e-6) and r.snr_db == pytest.approx(r1.snr_db, rel=2e-6)
 
 
 def test_single_process_multi_handle_search():
