@@ -28,8 +28,8 @@ struct SearchArgs {
     cf* scratch;           // L2-exchange variants: [groups][2][16][RS] (double-buffered finished rows)
     unsigned* group_ctr;   // coop variant: one arrival counter per CTA group (zeroed before the launch)
     Candidate* row_slots;  // coop variant: [groups][R] per-CTA partial row results
-    float* partial;        // coop variant: [groups][R][ACC_ELEMS] accumulators of row parts handed to the finishing group
-    unsigned* part_ctr;    // coop variant: [groups][R] hand-over arrivals (zeroed before the launch)
+    float* partial;        // coop variant: [groups][K-1][R][ACC_ELEMS] power planes of tail-row blocks handed to the finishing group
+    unsigned* part_ctr;    // coop variant: [groups][R] published planes (zeroed before the launch)
     int row_granular;      // coop variant: deal out whole rows only (no hand-over; sums independent of the group count)
 };
 
@@ -81,7 +81,7 @@ struct VariantOps {
     // cluster-free cooperative persistent variant: groups of R CTAs, software barriers through L2
     cudaError_t (*launch_search_coop)(const SearchArgs&, int groups, cudaStream_t);
     int (*max_groups_coop)();              // co-resident CTA groups on the current device
-    size_t partial_bytes_per_group;        // coop variant: one group's accumulator (all R slices)
+    size_t partial_bytes_per_group;        // coop variant: one power plane (all R slices) of the tail hand-over
 };
 
 // defined in gnss_q3.cu / gnss_q13.cu / gnss_q29.cu

@@ -497,6 +497,9 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
 __device__ __forceinline__ void group_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
+__device__ __forceinline__ void group_arrive_n(unsigned* ctr, unsigned n) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(n) : "memory");
+}
 __device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target) {
     // acquire polls.  (Relaxed polls + one acquire fence, with and without __nanosleep back-off, were
     // measured in r01 and were 1-2 % slower: the slower acquire poll is its own back-off.)
@@ -504,6 +507,49 @@ __device__ __forceinline__ void group_spin(const unsigned* ctr, unsigned target)
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     } while ((int)(v - target) < 0);
+}
+
+// Tail hand-over helpers of the cooperative kernel (cold: kept out of line so that the K loop's code and
+// register allocation stay what they are without them).
+template <int Q, int R, int T>
+__device__ __noinline__ void publish_plane(float* acc, float* dst, int tid) {
+    using SX = SplitX<Q, R>;
+    for (int j = tid; j < SX::P4_TASKS; j += T) {
+#pragma unroll
+        for (int ap = 0; ap < 16; ++ap) {
+            float2* p = reinterpret_cast<float2*>(acc + ap * SX::CHX + 2 * j);
+            __stcg(reinterpret_cast<float2*>(dst + ap * SX::CHX + 2 * j), *p);
+            *p = make_float2(0.f, 0.f);
+        }
+    }
+}
+template <int Q, int R, int T>
+__device__ __noinline__ void merge_planes(float* acc, const float* planes, int n_planes, int tid) {
+    constexpr int ACC4 = SplitX<Q, R>::ACC_ELEMS / 4;
+    const float4* src = reinterpret_cast<const float4*>(planes);
+    float4* a4 = reinterpret_cast<float4*>(acc);
+    int q = tid;
+    for (; q + T < ACC4; q += 2 * T) {             // two cells' chains at once: twice the loads in flight
+        float4 v = a4[q], w = a4[q + T];
+#pragma unroll 4
+        for (int k = 0; k < n_planes; ++k) {
+            const float4 o = __ldcg(src + (size_t)k * (R * ACC4) + q);
+            const float4 u = __ldcg(src + (size_t)k * (R * ACC4) + q + T);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            w.x += u.x; w.y += u.y; w.z += u.z; w.w += u.w;
+        }
+        a4[q] = v;
+        a4[q + T] = w;
+    }
+    for (; q < ACC4; q += T) {
+        float4 v = a4[q];
+#pragma unroll 8
+        for (int k = 0; k < n_planes; ++k) {
+            const float4 o = __ldcg(src + (size_t)k * (R * ACC4) + q);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        a4[q] = v;
+    }
 }
 
 // The software pipeline runs ACROSS row boundaries: passes 1-3 of the next row's first block overlap the
@@ -555,9 +601,10 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     // per group were measured 7 % slower at Q = 29).  The n_tail remaining rows are dealt out in units of one
     // block of one row, as contiguous ranges [tb(g), tb(g+1)) of u = tail_row*K + k, so every group gets the
     // same amount of the tail.  A tail row cut by a range boundary is finished by the group holding its first
-    // block; the groups holding its later parts leave their partial accumulators in HBM and arrive on a counter
-    // of the finishing group.  Those groups never wait for anything, so nobody waits on a waiter.  With
-    // row_granular the tail is dealt out as whole rows too (sums then do not depend on the group count).
+    // block; the groups holding its later blocks publish each block's power plane in HBM and arrive on a
+    // counter of the finishing group, which adds the planes in block order: the sum is bit-identical to an
+    // uncut row's, so results do not depend on how many rows (PRNs) the handle has.  Publishing groups never
+    // wait for anything, so nobody waits on a waiter.  row_granular: whole rows only (no planes needed).
     const int full = n_rows / ngroups, tail_base = full * ngroups, n_tail = n_rows - tail_base;
     auto tb = [&](int g) -> int {                  // 32-bit on purpose (a 64-bit division here costs the Q = 29 kernel
                                                    // 14 spilled registers); the host checks ngroups^2 * K < 2^32
@@ -581,6 +628,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     int i = 0, par = 0;
     const Part first = part(0);
     int left = first.ke - first.kb;                // blocks of part i still to do, this one included
+    bool later = first.kb > 0;                     // part i continues a row that an earlier group finishes
     for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
     SearchLoader ld = loader_of(first.row);
     ld.x += (size_t)first.kb * G::NX;
@@ -630,43 +678,31 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
         if (more)
             for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
-        const Part cp = last_of_part ? part(i) : Part{0, 0, 0};
-        const int row = cp.row;
-        if (last_of_part && cp.kb > 0) {
-            // a later part of a row some earlier group finishes: hand the partial accumulator over
-            __syncthreads();
-            float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)group * R + rank) * SX::ACC_ELEMS);
-            float4* a4 = reinterpret_cast<float4*>(acc);
-            for (int q = tid; q < SX::ACC_ELEMS / 4; q += T) {
-                __stcg(dst + q, a4[q]);
-                a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int gf = group - 1;                // the finisher: last group whose range starts at or before the row's
-                while (tb(gf) > (row - tail_base) * a.K) --gf;
-                group_arrive(a.part_ctr + (size_t)gf * R + rank);      // release, cumulative over the CTA barrier
+        if (later) {
+            // A later part of a tail row that an earlier group finishes: publish this block's power plane on
+            // its own (slot = block index in the row, in the finisher's slab), so that the finisher can add the
+            // planes one by one in block order -- bit for bit the sum an uncut row gets.  Every thread moves
+            // the columns its own pass-4 tasks accumulated (program order: no barrier) and re-zeroes them.
+            const Part cp = part(i);
+            const int kk = cp.ke - left;           // this block's index in its row
+            int gf = group - 1;                    // the finisher: last group whose range starts at or before the row's
+            while (tb(gf) > (cp.row - tail_base) * a.K) --gf;
+            float* dst = a.partial + (((size_t)gf * (a.K - 1) + (kk - 1)) * R + rank) * SX::ACC_ELEMS;
+            publish_plane<Q, R, T>(acc, dst, tid);
+            if (last_of_part) {
+                __syncthreads();
+                if (tid == 0) group_arrive_n(a.part_ctr + (size_t)gf * R + rank, (unsigned)(cp.ke - cp.kb));   // release
             }
         } else if (last_of_part) {
-            __syncthreads();                       // this group's blocks of `row` are in the accumulator
+            __syncthreads();                       // this group's blocks of the row are in the accumulator
+            const Part cp = part(i);
+            const int row = cp.row;
             if (cp.ke < a.K) {
-                // the remaining blocks were done by the following groups: add their parts, in block order
-                const int row_end = (row - tail_base + 1) * a.K;
-                int parts = 0, g_end = group + 1;  // (a group's range is empty when there are fewer units than groups)
-                for (; g_end < ngroups && tb(g_end) < row_end; ++g_end) parts += tb(g_end + 1) > tb(g_end);
-                if (tid == 0) group_spin(a.part_ctr + (size_t)group * R + rank, (unsigned)parts);
+                // blocks cp.ke .. K-1 were done by the following groups: add their planes in block order
+                if (tid == 0) group_spin(a.part_ctr + (size_t)group * R + rank, (unsigned)(a.K - cp.ke));
                 __syncthreads();
-                float4* a4 = reinterpret_cast<float4*>(acc);
-                for (int g2 = group + 1; g2 < g_end; ++g2) {
-                    if (tb(g2 + 1) <= tb(g2)) continue;
-                    const float4* src = reinterpret_cast<const float4*>(a.partial + ((size_t)g2 * R + rank) * SX::ACC_ELEMS);
-                    for (int q = tid; q < SX::ACC_ELEMS / 4; q += T) {
-                        const float4 o = __ldcg(src + q);
-                        float4 v = a4[q];
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                        a4[q] = v;
-                    }
-                }
+                merge_planes<Q, R, T>(acc, a.partial + (((size_t)group * (a.K - 1) + (cp.ke - 1)) * R + rank) * SX::ACC_ELEMS,
+                                      a.K - cp.ke, tid);
                 __syncthreads();
             }
             const int p = row % a.P, b = row / a.P;
@@ -771,6 +807,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         if (last_of_part) {
             const Part np = part(++i);
             left = np.ke - np.kb;
+            later = np.kb > 0;
         } else {
             --left;
         }

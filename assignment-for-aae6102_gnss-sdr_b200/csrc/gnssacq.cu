@@ -308,7 +308,7 @@ int validate(const gnssacq_config* c, std::string& why) {
     if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
     for (int i = 0; i < c->n_prn; ++i)
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
-    if (c->work_split < 0 || c->work_split > 1) { why = "work_split must be 0 (blocks) or 1 (whole rows)"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->work_split < 0 || c->work_split > 2) { why = "work_split must be 0 (auto), 1 (whole rows) or 2 (block-granular tail)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->exchange < 0 || c->exchange > 3) { why = "exchange must be 0 (auto), 1 (DSMEM), 2 (L2 + clusters) or 3 (L2 + cooperative groups)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
         why = "samples_per_ms must be 2000*Q (built: Q = 3, 13, 29 -> 6000, 26000, 58000)";
@@ -465,7 +465,17 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         int n = xmode == 3 ? ops->max_groups_coop() : ops->max_clusters_l2x();
         // the cooperative kernel deals out single blocks of a row (work_split 0) or whole rows (1); the
         // clustered one whole rows
-        const bool by_blocks = xmode == 3 && !cfg->work_split && (unsigned long long)n * n * h->K < (1ull << 32);
+        // Block-granular tail (see search_kernel_coop): needs K-1 power planes per group (150 MB at the
+        // reference's sizes) -- not possible above 2 GiB or beyond the kernel's 32-bit unit arithmetic.  It
+        // costs 0.15-0.4 row times (publishing and adding the planes), so work_split 0 (auto) uses it only
+        // where whole rows would leave >= 4 % of the last round's group-time idle (measured r01: pays for
+        // <= 8 PRNs at N = 26 000, <= 4 PRNs at N = 58 000, not for 32).  Results are identical either way.
+        bool by_blocks = xmode == 3 && cfg->work_split != 1 && h->K > 1 && (unsigned long long)n * n * h->K < (1ull << 32) &&
+                         (unsigned long long)n * (h->K - 1) * ops->partial_bytes_per_group <= (2ull << 30);
+        if (by_blocks && cfg->work_split == 0) {
+            const long long rows = (long long)h->P * h->B, rounds = (rows + n - 1) / n;
+            by_blocks = (double)(rounds * n - rows) >= 0.04 * (double)(rounds * n);
+        }
         const long long max_useful = by_blocks ? (long long)h->P * h->B * h->K : (long long)h->P * h->B;
         if (n > max_useful) n = (int)max_useful;
         if (n <= 0) {
@@ -475,24 +485,28 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         if (xmode == 3) h->coop_groups = n; else h->l2x_clusters = n;
         CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
         // the padding columns of the exchange layout are never written: they must read as exact zeros
-        CUC(cudaMemset(h->d_scratch, 0, (size_t)n * ops->scratch_bytes_per_cluster));
+        CUC(cudaMemsetAsync(h->d_scratch, 0, (size_t)n * ops->scratch_bytes_per_cluster, h->stream));
         CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * (1 + ops->R) * sizeof(unsigned)));     // group barriers + hand-over counters
-        if (by_blocks) CUC(cudaMalloc(&h->d_partial, (size_t)n * ops->partial_bytes_per_group));
+        if (by_blocks) CUC(cudaMalloc(&h->d_partial, (size_t)n * (h->K - 1) * ops->partial_bytes_per_group));
         CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
     if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
     CUC(cudaMallocHost(&h->h_if, h->if_bytes));
     CUC(cudaMallocHost(&h->h_res, h->P * sizeof(gnssacq_result)));
-    CUC(cudaMemcpy(h->d_bin_base, h->bin_base.data(), h->B * sizeof(int), cudaMemcpyHostToDevice));
-    CUC(cudaMemcpy(h->d_bin_shift, h->bin_shift.data(), h->B * sizeof(int), cudaMemcpyHostToDevice));
-    CUC(cudaMemcpy(h->d_prn, cfg->prn, h->P * sizeof(int), cudaMemcpyHostToDevice));
-    CUC(cudaMemcpy(h->d_base_freq, h->base_freq.data(), nb * sizeof(double), cudaMemcpyHostToDevice));
+    // Every create-time copy goes on the handle's own (non-blocking) stream: a synchronous cudaMemcpy from
+    // pageable memory returns once the data is STAGED, and its DMA on the legacy stream is not ordered with
+    // kernels on a non-blocking stream (seen once in r01 as one PRN's code spectrum built from a half-copied
+    // replica table).
+    CUC(cudaMemcpyAsync(h->d_bin_base, h->bin_base.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaMemcpyAsync(h->d_bin_shift, h->bin_shift.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaMemcpyAsync(h->d_prn, cfg->prn, h->P * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaMemcpyAsync(h->d_base_freq, h->base_freq.data(), nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
 
     // code tables -> HBM, then K0 fills the conj-spectrum cache
     {
         std::vector<int8_t> sc((size_t)h->P * N);
         for (int p = 0; p < h->P; ++p) code_replica(*cfg, cfg->prn[p], sc.data() + (size_t)p * N);
-        CUC(cudaMemcpy(h->d_scode, sc.data(), sc.size(), cudaMemcpyHostToDevice));
+        CUC(cudaMemcpyAsync(h->d_scode, sc.data(), sc.size(), cudaMemcpyHostToDevice, h->stream));
         CodeArgs a{h->d_scode, h->d_cc};
         CUC(ops->launch_code(a, h->P, h->stream));
         CUC(cudaStreamSynchronize(h->stream));
@@ -550,9 +564,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.row_slots = h->d_row_slots;
     sa.partial = h->d_partial;
     sa.part_ctr = h->d_group_ctr ? h->d_group_ctr + h->coop_groups : nullptr;
-    // (the kernel's unit arithmetic is 32-bit: groups^2 * K must stay below 2^32, else deal out whole rows)
-    sa.row_granular = (h->cfg.work_split || !h->d_partial ||
-                       (unsigned long long)h->coop_groups * h->coop_groups * h->K >= (1ull << 32)) ? 1 : 0;
+    sa.row_granular = h->d_partial ? 0 : 1;
     if (h->coop_groups > 0) {
         CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * (1 + h->ops->R) * sizeof(unsigned), s));
         CU(h->ops->launch_search_coop(sa, h->coop_groups, s));
@@ -611,6 +623,7 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
         st->threads = h->ops->T;
         st->exchange = h->coop_groups > 0 ? 3 : (h->l2x_clusters > 0 ? 2 : 1);
         st->resident_clusters = h->coop_groups > 0 ? h->coop_groups : h->l2x_clusters;
+        st->work_split = h->d_partial ? 2 : 1;
     }
     return GNSSACQ_OK;
 }
@@ -712,7 +725,8 @@ int gnssacq_fine_frequency(gnssacq_handle* h, const void* if_long, size_t nbytes
         CUF(cudaMalloc(&h->d_fine_start, GNSSACQ_MAX_PRN * sizeof(int)));
         CUF(cudaMalloc(&h->d_fine_best, GNSSACQ_MAX_PRN * sizeof(unsigned long long)));
         CUF(cudaMalloc(&h->d_fine_u, (size_t)kChunk * K * L * N * sizeof(cf)));
-        CUF(cudaMemcpy(h->d_fine_chip, chip.data(), chip.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUF(cudaMemcpyAsync(h->d_fine_chip, chip.data(), chip.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        CUF(cudaStreamSynchronize(s));                                          // `chip` is a temporary
         h->fine_L = L;
     }
     if (n_sv > GNSSACQ_MAX_PRN) return fail(h, GNSSACQ_ERR_INVALID_ARG, "too many SVs");

@@ -62,6 +62,7 @@ class Stats(C.Structure):
         ("finalize_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
         ("kernel_launches", C.c_int32), ("n_bases", C.c_int32), ("cluster_ctas", C.c_int32),
         ("threads", C.c_int32), ("exchange", C.c_int32), ("resident_clusters", C.c_int32),
+        ("work_split", C.c_int32),
     ]
 
     def as_dict(self) -> dict:

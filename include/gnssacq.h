@@ -65,10 +65,12 @@ typedef struct gnssacq_config {
                                  buffer (persistent clusters), 3 = L2-resident buffer, cooperative CTA
                                  groups without clusters (uses every SM) */
     int32_t work_split;       /* exchange 3 only: how the (PRN, bin) rows are dealt out to the resident CTA groups.
-                                 0 = block-granular (default): a row's noncoh_blocks may be shared by consecutive
-                                 groups whose partial sums are added in block order -- every group gets the same
-                                 work, but the last bits of peak/SNR depend on how many rows the handle has;
-                                 1 = whole rows: a PRN's result is bit-identical whatever shard it is part of */
+                                 1 = whole rows.  2 = whole rows while there are enough for every group, the
+                                 remaining rows block by block: consecutive groups share a row's noncoh_blocks and
+                                 the finishing group adds their power planes in block order (bit-identical to 1;
+                                 costs (noncoh_blocks - 1) planes of samples_per_ms floats per group of HBM).
+                                 0 = auto: 2 where it pays -- a handle with few rows (one rank's shard at 8 GPUs,
+                                 a single-PRN re-acquisition) --, else 1 */
 } gnssacq_config;
 
 /* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */
@@ -98,6 +100,7 @@ typedef struct gnssacq_stats {
     int32_t threads;
     int32_t exchange;         /* 1 = DSMEM, 2 = L2 + clusters, 3 = L2 + cooperative groups */
     int32_t resident_clusters;/* persistent clusters / CTA groups of the search kernel (0 for DSMEM) */
+    int32_t work_split;       /* schedule actually used: 1 = whole rows, 2 = block-granular tail */
 } gnssacq_stats;
 
 typedef struct gnssacq_handle gnssacq_handle;

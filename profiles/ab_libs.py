@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 CHILD = r'''
+import os
 import sys
 sys.path[:0] = ["/root/repo", "/root/repo/assignment-for-aae6102_gnss-sdr_b200"]
 import gnssacq
@@ -15,7 +16,7 @@ for which in ("urban", "opensky"):
     spec, fs, if_hz = (urban_recording(), 26e6, 0.0) if which == "urban" else (opensky_recording(), 58e6, 4.58e6)
     raw = spec.read(0, 20)
     for n in prns:
-        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1))) as s:
+        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}))) as s:
             best = 1e9
             for _ in range(8):
                 s.search(raw)
@@ -34,7 +35,9 @@ for i, a in enumerate(sys.argv):
 best = {}
 for r in range(rounds):
     for name, path in libs:
-        env = dict(os.environ, GNSSACQ_LIB=os.path.abspath(path))
+        env = dict(os.environ, GNSSACQ_LIB=os.path.abspath(path.split("@")[0]))
+        if "@" in path:                                  # name=lib.so@1 -> work_split=1
+            env["AB_WORK_SPLIT"] = path.split("@")[1]
         out = subprocess.run([sys.executable, "-c", CHILD, prns], env=env, capture_output=True, text=True)
         if out.returncode:
             print(name, "FAILED", out.stderr[-500:])

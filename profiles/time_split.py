@@ -11,7 +11,7 @@ for which in (sys.argv[1:] or ["urban", "opensky"]):
     raw = spec.read(0, 20)
     for n_prn in (1, 2, 4, 8, 16, 32):
         out = []
-        for split in (1, 0):
+        for split in (1, 2):
             cfg = gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n_prn + 1), work_split=split)
             with api.Searcher(cfg) as s:
                 best = tot = 1e9

@@ -274,18 +274,17 @@ def test_full_depth_k20_subset_against_oracle(shape, prns):
     with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
         rows = s.search(raw_b)
     assert_rows_match(rows, ref, what=f"{shape} K=20")
-    # work_split=1 deals out whole rows: PRN sharding then never changes a row (bytes identical)
-    with api.Searcher(cfg_from(file, signal, acq, prns, work_split=1)) as s:
-        rows1 = s.search(raw_b)
-    assert_rows_match(rows1, ref, what=f"{shape} K=20 whole rows")
-    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)), work_split=1)) as s:
+    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)))) as s:
         full = {r.prn: r for r in s.search(raw_b)}
-    for r in rows1:
+    for r in rows:                                   # PRN sharding never changes a row (bytes identical)
         assert bytes(full[r.prn]) == bytes(r)
-    # the default block-granular split only changes the order of the K additions per cell
-    for r, r1 in zip(rows, rows1):
-        assert (r.prn, r.code_phase, r.doppler_bin, r.acquired) == (r1.prn, r1.code_phase, r1.doppler_bin, r1.acquired)
-        assert r.peak == pytest.approx(r1.peak, rel=2e-6) and r.snr_db == pytest.approx(r1.snr_db, rel=2e-6)
+    # ... and neither does the schedule: whole rows per CTA group and the block-granular tail give the same bytes
+    for ws in (1, 2):
+        with api.Searcher(cfg_from(file, signal, acq, prns, work_split=ws)) as s:
+            assert [bytes(r) for r in s.search(raw_b)] == [bytes(r) for r in rows]
+            assert s.last_stats.work_split == ws
+    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)), work_split=2)) as s:
+        assert all(bytes(full[r.prn]) == bytes(r) for r in s.search(raw_b))
 
 
 @pytest.mark.parametrize("n,variant,datalen,prns", [
@@ -296,8 +295,8 @@ def test_full_depth_k20_subset_against_oracle(shape, prns):
 ])
 def test_block_granular_split_of_few_rows(n, variant, datalen, prns):
     """Few rows on many resident CTA groups (one rank's shard at 8 GPUs, a single-PRN re-acquisition): the
-    cooperative kernel cuts rows at block granularity and the finishing group adds the handed-over partial
-    accumulators.  Rows against the oracle, and against the whole-row schedule of the same kernel."""
+    cooperative kernel cuts tail rows at block granularity and the finishing group adds the published power
+    planes in block order.  Rows against the oracle, and byte for byte against the whole-row schedule."""
     if n == 6000:
         fs, if_hz = 6e6, 1.25e6
         file, signal, acq = structs(fs, if_hz, datalen=datalen)
@@ -310,17 +309,19 @@ def test_block_granular_split_of_few_rows(n, variant, datalen, prns):
         file.dataType, file.dataPrecision = 2, 1
     ref = oracle_rows(raw_b, file, signal, acq, prns)
     kw = dict(cluster_ctas=variant[0], threads=variant[1], exchange=variant[2])
-    with api.Searcher(cfg_from(file, signal, acq, prns, **kw)) as s:
+    with api.Searcher(cfg_from(file, signal, acq, prns, work_split=2, **kw)) as s:
         rows = s.search(raw_b)
         again = s.search(raw_b)
         groups = s.last_stats.resident_clusters
+        assert s.last_stats.work_split == (2 if datalen > 1 else 1)
     assert [bytes(r) for r in rows] == [bytes(r) for r in again]          # deterministic
     assert_rows_match(rows, ref, what=f"N={n} {variant} K={datalen} {len(prns)} PRN on {groups} groups")
     with api.Searcher(cfg_from(file, signal, acq, prns, work_split=1, **kw)) as s:
         rows1 = s.search(raw_b)
-    for r, r1 in zip(rows, rows1):
-        assert (r.prn, r.code_phase, r.doppler_bin, r.acquired) == (r1.prn, r1.code_phase, r1.doppler_bin, r1.acquired)
-        assert r.peak == pytest.approx(r1.peak, rel=2e-6) and r.snr_db == pytest.approx(r1.snr_db, rel=2e-6)
+        assert s.last_stats.work_split == 1
+    assert [bytes(r) for r in rows] == [bytes(r) for r in rows1]
+    with api.Searcher(cfg_from(file, signal, acq, prns, **kw)) as s:              # auto: either schedule, same bytes
+        assert [bytes(r) for r in s.search(raw_b)] == [bytes(r) for r in rows1]
 
 
 def test_single_process_multi_handle_search():
