@@ -342,3 +342,21 @@ def test_single_process_multi_handle_search():
         for p in parts:
             p.close()
     assert [bytes(r) for r in rows] == full
+
+
+def test_fresh_handles_agree():
+    """Regression (r01): the replica table was copied with a synchronous cudaMemcpy from pageable memory, which
+    returns when the data is staged, and K0 ran on the handle's non-blocking stream -- about one handle in ten
+    built the last PRNs' code spectra from a half-copied table.  Every fresh handle must give the same bytes."""
+    file, signal, acq = structs(26e6, 0.0, datalen=2)
+    raw_b = synth_if(urban_spec(), 0, 2)
+    prns = list(range(1, 33))
+    first = None
+    for variant in [(4, 256, 1), (0, 0, 0)]:
+        for _ in range(40):
+            with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=variant[0], threads=variant[1],
+                                       exchange=variant[2])) as s:
+                got = [bytes(r) for r in s.search(raw_b)]
+            if first is None:
+                first = got
+            assert got == first
