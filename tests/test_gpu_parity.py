@@ -351,8 +351,8 @@ def test_fresh_handles_agree():
     file, signal, acq = structs(26e6, 0.0, datalen=2)
     raw_b = synth_if(urban_spec(), 0, 2)
     prns = list(range(1, 33))
-    first = None
     for variant in [(4, 256, 1), (0, 0, 0)]:
+        first = None
         for _ in range(40):
             with api.Searcher(cfg_from(file, signal, acq, prns, cluster_ctas=variant[0], threads=variant[1],
                                        exchange=variant[2])) as s:
