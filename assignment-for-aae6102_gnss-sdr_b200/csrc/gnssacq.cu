@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -234,6 +235,13 @@ struct gnssacq_handle {
     int8_t* d_fine_ca = nullptr;
     int* d_fine_start = nullptr;
     unsigned long long* d_fine_best = nullptr;
+    // re-acquisition sweep (gnssacq_sweep): second staging pair, copy stream, per-buffer events, result slab
+    void* d_if2 = nullptr;
+    void* h_if2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    gnssacq_result* d_res_sweep = nullptr;
+    int sweep_cap = 0;
     // pinned host
     void* h_if = nullptr;
     gnssacq_result* h_res = nullptr;
@@ -371,7 +379,12 @@ int gnssacq_destroy(gnssacq_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
     cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
-    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_partial); cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_partial); cudaFree(h->d_if2); cudaFree(h->d_res_sweep);
+    if (h->h_if2) cudaFreeHost(h->h_if2);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& e : h->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_consumed) if (e) cudaEventDestroy(e);
+    cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca); cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
     if (h->h_if) cudaFreeHost(h->h_if);
@@ -666,6 +679,73 @@ int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n, const void* if_sa
         int rc = gnssacq_fetch_results(hs[i], out + off, nullptr);
         if (rc != GNSSACQ_OK) return rc;
         off += (size_t)hs[i]->P;
+    }
+    return GNSSACQ_OK;
+}
+
+// BASELINE config 4 (periodic re-acquisition over a long recording) / SURVEY 8f-3 (IF ingest): n_windows
+// independent searches.  Window i+1 is staged (host memcpy into pinned memory) and copied to HBM on a copy
+// stream while window i is searched; two staging pairs, events in both directions, one D2H of all rows at the
+// end.  Rows of window i are out[i*n_prn .. (i+1)*n_prn) and equal what gnssacq_search returns for that window.
+int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
+                  gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !windows || !out || n_windows < 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (nbytes_each < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "window shorter than noncoh_blocks*coh_ms ms");
+    for (int i = 0; i < n_windows; ++i)
+        if (!windows[i]) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL window");
+    if (n_windows == 0) return GNSSACQ_OK;
+    CU(cudaSetDevice(h->device));
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&h->d_if2, h->if_bytes));
+        CU(cudaMallocHost(&h->h_if2, h->if_bytes));
+        for (auto& e : h->ev_copied) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : h->ev_consumed) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (h->sweep_cap < n_windows) {
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_res_sweep);
+        h->d_res_sweep = nullptr;
+        h->sweep_cap = 0;
+        CU(cudaMalloc(&h->d_res_sweep, (size_t)n_windows * h->P * sizeof(gnssacq_result)));
+        h->sweep_cap = n_windows;
+    }
+    void* d_buf[2] = {h->d_if, h->d_if2};
+    void* h_buf[2] = {h->h_if, h->h_if2};
+    const auto t0 = std::chrono::steady_clock::now();
+    int launches = 0;
+    for (int i = 0; i < n_windows; ++i) {
+        const int b = i & 1;
+        if (i >= 2) CU(cudaEventSynchronize(h->ev_copied[b]));              // pinned buffer b has left for HBM
+        std::memcpy(h_buf[b], windows[i], h->if_bytes);
+        if (i >= 2) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[b], 0));   // search i-2 is done with d_buf[b]
+        else CU(cudaStreamWaitEvent(h->copy_stream, h->ev[4], 0));          // (first use: after whatever ran last)
+        CU(cudaMemcpyAsync(d_buf[b], h_buf[b], h->if_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
+        h->have_h2d = false;
+        CU(cudaEventRecord(h->ev[0], h->stream));
+        int rc = enqueue(h, d_buf[b], h->d_res_sweep + (size_t)i * h->P);
+        if (rc != GNSSACQ_OK) return rc;
+        launches += h->launches;
+        CU(cudaEventRecord(h->ev_consumed[b], h->stream));
+    }
+    CU(cudaMemcpyAsync(out, h->d_res_sweep, (size_t)n_windows * h->P * sizeof(gnssacq_result), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        cudaEventElapsedTime(&st->wipeoff_fft_ms, h->ev[1], h->ev[2]);      // (of the last window)
+        cudaEventElapsedTime(&st->search_ms, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&st->finalize_ms, h->ev[3], h->ev[4]);
+        st->kernel_launches = launches;
+        st->n_bases = (int)h->base_freq.size();
+        st->cluster_ctas = h->ops->R;
+        st->threads = h->ops->T;
+        st->exchange = h->coop_groups > 0 ? 3 : (h->l2x_clusters > 0 ? 2 : 1);
+        st->resident_clusters = h->coop_groups > 0 ? h->coop_groups : h->l2x_clusters;
+        st->work_split = h->d_partial ? 2 : 1;
     }
     return GNSSACQ_OK;
 }

@@ -74,7 +74,7 @@ EXPORTS = (
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
-    "gnssacq_search_multi",
+    "gnssacq_search_multi", "gnssacq_sweep",
 )
 
 
@@ -105,6 +105,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
     lib.gnssacq_fine_frequency.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32, vp, vp, vp]
     lib.gnssacq_search_multi.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_size_t, C.POINTER(Result)]
+    lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
@@ -231,6 +232,21 @@ class Searcher:
         self._check(lib.gnssacq_search(self._h, buf.ctypes.data, buf.nbytes, out, C.byref(st)))
         self.last_stats = st
         return list(out)
+
+    def sweep(self, windows) -> List[List[Result]]:
+        """Re-acquisition sweep: one search per host window (bytes-like), copies overlapped with the searches."""
+        bufs = [np.ascontiguousarray(np.frombuffer(w, dtype=np.uint8) if not isinstance(w, np.ndarray) else w)
+                for w in windows]
+        n, p = len(bufs), self.cfg.n_prn
+        if n == 0:
+            return []
+        each = min(b.nbytes for b in bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        out = (Result * (n * p))()
+        st = Stats()
+        self._check(lib.gnssacq_sweep(self._h, ptrs, n, each, out, C.byref(st)))
+        self.last_stats = st
+        return [list(out[i * p:(i + 1) * p]) for i in range(n)]
 
     def search_device(self, dev_ptr: int, nbytes: int) -> List[Result]:
         out = (Result * self.cfg.n_prn)()

@@ -154,6 +154,16 @@ int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if_samples, size
 int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n_handles, const void* if_samples, size_t nbytes,
                          gnssacq_result* out);
 
+/* Re-acquisition sweep (BASELINE.json config 4; replaces a loop of SDR_main.m:17-23 over file.skip; the IF
+ * ingest of SURVEY 8f-3, acquisition.m:27-38).  `windows[i]` points to the i-th window's IF bytes in HOST memory
+ * (what acquisition.m would fread after fseek to skip_i*Sample*dataPrecision*dataType), each at least
+ * gnssacq_if_bytes long.  Window i+1 is staged in pinned memory and copied to HBM on a copy stream while window i
+ * is searched; all rows come back in one transfer: out[i*n_prn + p] is what gnssacq_search returns for window i.
+ * stats (may be NULL): total_ms = host wall time of the sweep, kernel_launches = all launches, kernel times of
+ * the last window. */
+int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
+                  gnssacq_result* out, gnssacq_stats* stats);
+
 /* Fine-frequency stage (replaces acquisition.m:89-121).  `if_long` is the (L+1) ms block
  * acquisition.m:91/96 reads from the same file offset (host memory); for each of the n_sv acquired SVs
  * (prn[i], code_phase[i] = Acquired.codedelay) the code-stripped L ms are zero-padded to

@@ -93,6 +93,7 @@ def test_null_arguments_are_errors_not_crashes():
     assert api.lib.gnssacq_config_default(None) == -1
     assert api.lib.gnssacq_if_bytes(None) == 0
     assert api.lib.gnssacq_search(None, None, 0, None, None) == -1
+    assert api.lib.gnssacq_sweep(None, None, 0, 0, None, None) == -1
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -360,3 +360,32 @@ def test_fresh_handles_agree():
             if first is None:
                 first = got
             assert got == first
+
+
+@pytest.mark.parametrize("n,datalen,n_windows", [(6000, 2, 5), (26000, 2, 4), (58000, 1, 3)])
+def test_reacquisition_sweep_equals_single_searches(n, datalen, n_windows):
+    """gnssacq_sweep (BASELINE config 4: a window every 100 ms, copies overlapped with the searches): every
+    window's rows are the bytes gnssacq_search gives for that window, and window 0 matches the oracle."""
+    if n == 6000:
+        fs, if_hz = 6e6, 1.25e6
+        file, signal, acq = structs(fs, if_hz, datalen=datalen)
+        spec = small_spec(fs, if_hz, n)
+    else:
+        shape = "urban" if n == 26000 else "opensky"
+        file, signal, acq = gnssacq.initParameters(shape=shape)
+        acq.datalen = datalen
+        spec = urban_spec() if shape == "urban" else opensky_spec()
+    windows = [synth_if(spec, 100 * j, datalen) for j in range(n_windows)]
+    file.dataType, file.dataPrecision = 2, 1
+    prns = [1, 3, 7, 16, 22, 30]
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        single = [[bytes(r) for r in s.search(w)] for w in windows]
+        swept = s.sweep(windows)
+        assert s.last_stats.kernel_launches >= 3 * n_windows
+        assert [[bytes(r) for r in rows] for rows in swept] == single
+        assert s.sweep([]) == []
+        again = s.sweep(windows[::-1])                                  # buffers are reused correctly
+        assert [[bytes(r) for r in rows] for rows in again] == single[::-1]
+        with pytest.raises(gnssacq.GnssAcqError):
+            s.sweep([windows[0][:-2]])
+    assert_rows_match(swept[0], oracle_rows(windows[0], file, signal, acq, prns), what=f"sweep N={n} window 0")
