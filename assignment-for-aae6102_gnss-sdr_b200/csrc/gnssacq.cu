@@ -197,6 +197,123 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
 
 }  // namespace
 
+// ---------------------------------------------------------------- tracking correlators
+// trackingCT.m:85-118 for a batch of channels: numSample samples from the channel's position in the resident
+// recording, carrier replica exp(i(2 pi f n/Fs + remPhase)) (:103-106), "Inphase" = imag(x.*carr), "Quadrature"
+// = real(x.*carr) (:112-113), code replicas Code(ceil(t)+1), t = spacing + remChip + n*codeFreq/Fs (:96-101), and
+// the sums per tap (:115-117).  Float64 throughout, like the reference: the kernel is latency-, not flop-bound.
+constexpr int kTrackMaxChannels = 64, kTrackMaxTaps = 32, kTrackChunks = 32, kTrackTapsPerThread = 8, kTrackThreads = 256;
+
+struct TrackArgs {
+    const void* raw;
+    int data_type, precision;
+    double fs_hz;
+    const gnssacq_channel* ch;
+    int n_taps;
+    const double* spacing;
+    const int8_t* ca;
+    const double* mean;       // [channels][2] (int16 path) or nullptr
+    double* partial;          // [channels][kTrackChunks][n_taps][2]
+};
+
+__device__ __forceinline__ void track_sample(const TrackArgs& a, long long idx, double mi, double mq, double& xr, double& xi) {
+    if (a.precision == 2) {
+        const int16_t* p = (const int16_t*)a.raw;
+        xr = (double)p[2 * idx] - mi;
+        xi = (double)p[2 * idx + 1] - mq;
+    } else if (a.data_type == 2) {
+        const char2 v = ((const char2*)a.raw)[idx];
+        xr = (double)v.x;
+        xi = (double)v.y;
+    } else {
+        xr = (double)((const int8_t*)a.raw)[idx];
+        xi = 0.0;
+    }
+}
+
+// trackingCT.m:90-92: per-integration DC of the int16 I and Q streams (exact integer sums)
+__global__ void __launch_bounds__(kTrackThreads) track_mean_kernel(TrackArgs a, double* __restrict__ mean) {
+    __shared__ long long sh[2][kTrackThreads / 32];
+    const gnssacq_channel c = a.ch[blockIdx.x];
+    const int16_t* p = (const int16_t*)a.raw + 2 * c.sample_offset;
+    long long si = 0, sq = 0;
+    for (int n = threadIdx.x; n < c.num_samples; n += kTrackThreads) { si += p[2 * n]; sq += p[2 * n + 1]; }
+    for (int off = 16; off; off >>= 1) { si += __shfl_down_sync(0xffffffffu, si, off); sq += __shfl_down_sync(0xffffffffu, sq, off); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = si; sh[1][threadIdx.x >> 5] = sq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        si = sq = 0;
+        for (int w = 0; w < kTrackThreads / 32; ++w) { si += sh[0][w]; sq += sh[1][w]; }
+        mean[2 * blockIdx.x] = (double)si / (double)c.num_samples;
+        mean[2 * blockIdx.x + 1] = (double)sq / (double)c.num_samples;
+    }
+}
+
+// grid (chunk, channel, tap group of 8)
+__global__ void __launch_bounds__(kTrackThreads) correlate_kernel(TrackArgs a) {
+    __shared__ double sh[kTrackThreads / 32][2 * kTrackTapsPerThread];
+    const int cidx = blockIdx.y, tap0 = blockIdx.z * kTrackTapsPerThread;
+    const gnssacq_channel c = a.ch[cidx];
+    const int per = (c.num_samples + kTrackChunks - 1) / kTrackChunks;
+    const int n_begin = blockIdx.x * per, n_end = min(n_begin + per, c.num_samples);
+    const double step = c.code_hz / a.fs_hz;
+    const double mi = a.mean ? a.mean[2 * cidx] : 0.0, mq = a.mean ? a.mean[2 * cidx + 1] : 0.0;
+    const int8_t* ca = a.ca + (size_t)(c.prn - 1) * 1023;
+    double off[kTrackTapsPerThread], acc_i[kTrackTapsPerThread], acc_q[kTrackTapsPerThread];
+#pragma unroll
+    for (int t = 0; t < kTrackTapsPerThread; ++t) {
+        off[t] = (0.0 + (tap0 + t < a.n_taps ? a.spacing[tap0 + t] : 0.0)) + c.rem_chip;     // (0 + Spacing + remChip), :96
+        acc_i[t] = acc_q[t] = 0.0;
+    }
+    for (int n = n_begin + threadIdx.x; n < n_end; n += kTrackThreads) {
+        double xr, xi;
+        track_sample(a, c.sample_offset + n, mi, mq, xr, xi);
+        // (explicit roundings: no FMA contraction, so every intermediate is the double the reference forms)
+        const double wave = __dadd_rn(__dmul_rn(2.0 * 3.14159265358979323846, __dmul_rn(c.carrier_hz, (double)n / a.fs_hz)), c.rem_phase);   // :103-104
+        double sn, cs;
+        sincos(wave, &sn, &cs);
+        const double inph = xr * sn + xi * cs;       // imag(x * exp(i wave))
+        const double quad = xr * cs - xi * sn;       // real(...)
+#pragma unroll
+        for (int t = 0; t < kTrackTapsPerThread; ++t) {
+            const double tt = __dadd_rn(off[t], __dmul_rn(step, (double)n));
+            long long k = (long long)ceil(tt) - 1;                  // Code(ceil(t)+1) of [Code(end) Code Code(1)] = CA[(ceil(t)-1) mod 1023]
+            k %= 1023;
+            if (k < 0) k += 1023;
+            const double chip = (double)ca[k];
+            acc_i[t] += chip * inph;
+            acc_q[t] += chip * quad;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kTrackTapsPerThread; ++t) {
+        for (int o = 16; o; o >>= 1) {
+            acc_i[t] += __shfl_down_sync(0xffffffffu, acc_i[t], o);
+            acc_q[t] += __shfl_down_sync(0xffffffffu, acc_q[t], o);
+        }
+        if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][2 * t] = acc_i[t]; sh[threadIdx.x >> 5][2 * t + 1] = acc_q[t]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kTrackTapsPerThread) {
+        const int t = tap0 + threadIdx.x / 2;
+        if (t < a.n_taps) {
+            double v = 0.0;
+            for (int w = 0; w < kTrackThreads / 32; ++w) v += sh[w][threadIdx.x];
+            a.partial[(((size_t)cidx * kTrackChunks + blockIdx.x) * a.n_taps + t) * 2 + (threadIdx.x & 1)] = v;
+        }
+    }
+}
+
+// fixed-order sum of the chunk partials (deterministic), out[channel][tap][I,Q]
+__global__ void correlate_finish_kernel(const double* __restrict__ partial, int n_taps, int n_elems, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;           // channel * n_taps*2 + tap*2 + iq
+    if (e >= n_elems) return;
+    const int per = n_taps * 2, c = e / per, r = e - c * per;
+    double v = 0.0;
+    for (int k = 0; k < kTrackChunks; ++k) v += partial[((size_t)c * kTrackChunks + k) * per + r];
+    out[e] = v;
+}
+
 // ---------------------------------------------------------------- handle
 struct gnssacq_handle {
     gnssacq_config cfg;
@@ -242,6 +359,17 @@ struct gnssacq_handle {
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
     gnssacq_result* d_res_sweep = nullptr;
     int sweep_cap = 0;
+    // tracking correlators (gnssacq_track_load / gnssacq_correlate): resident recording segment, C/A table,
+    // per-call channel table and partial sums
+    void* d_trk_raw = nullptr;
+    size_t trk_bytes = 0, trk_cap = 0;
+    int8_t* d_trk_ca = nullptr;            // [GNSSACQ_TRACK_MAX_PRN][1023]
+    void* d_trk_ch = nullptr;              // [kTrackMaxChannels] gnssacq_channel
+    double* d_trk_spacing = nullptr;       // [kTrackMaxTaps]
+    double* d_trk_partial = nullptr;       // [channels][chunks][taps][2]
+    double* d_trk_out = nullptr;           // [channels][taps][2]
+    double* d_trk_mean = nullptr;          // [channels][2] int16 path
+    double* h_trk_out = nullptr;           // pinned
     // pinned host
     void* h_if = nullptr;
     gnssacq_result* h_res = nullptr;
@@ -385,6 +513,9 @@ int gnssacq_destroy(gnssacq_handle* h) {
     for (auto& e : h->ev_copied) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_consumed) if (e) cudaEventDestroy(e);
     cudaFree(h->d_sums); cudaFree(h->d_means);
+    cudaFree(h->d_trk_raw); cudaFree(h->d_trk_ca); cudaFree(h->d_trk_ch); cudaFree(h->d_trk_spacing); cudaFree(h->d_trk_partial);
+    cudaFree(h->d_trk_out); cudaFree(h->d_trk_mean);
+    if (h->h_trk_out) cudaFreeHost(h->h_trk_out);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca); cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
     if (h->h_if) cudaFreeHost(h->h_if);
@@ -747,6 +878,83 @@ int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windo
         st->resident_clusters = h->coop_groups > 0 ? h->coop_groups : h->l2x_clusters;
         st->work_split = h->d_partial ? 2 : 1;
     }
+    return GNSSACQ_OK;
+}
+
+// Tracking correlators, SURVEY 8f-2.  gnssacq_track_load keeps a segment of the recording resident in HBM;
+// gnssacq_correlate then runs one integration period for a batch of channels against it.
+int gnssacq_track_load(gnssacq_handle* h, const void* if_samples, size_t nbytes) {
+    if (!h || !if_samples || nbytes == 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->trk_cap < nbytes) {
+        cudaFree(h->d_trk_raw);
+        h->d_trk_raw = nullptr;
+        h->trk_cap = h->trk_bytes = 0;
+        if (cudaMalloc(&h->d_trk_raw, nbytes) != cudaSuccess) { cudaGetLastError(); return fail(h, GNSSACQ_ERR_NOMEM, "recording segment does not fit in HBM"); }
+        h->trk_cap = nbytes;
+    }
+    if (!h->d_trk_ca) {
+        std::vector<int8_t> ca((size_t)GNSSACQ_TRACK_MAX_PRN * 1023);
+        for (int p = 1; p <= GNSSACQ_TRACK_MAX_PRN; ++p) ca_chips(p, ca.data() + (size_t)(p - 1) * 1023);
+        CU(cudaMalloc(&h->d_trk_ca, ca.size()));
+        CU(cudaMalloc(&h->d_trk_ch, kTrackMaxChannels * sizeof(gnssacq_channel)));
+        CU(cudaMalloc(&h->d_trk_spacing, kTrackMaxTaps * sizeof(double)));
+        CU(cudaMalloc(&h->d_trk_partial, (size_t)kTrackMaxChannels * kTrackChunks * kTrackMaxTaps * 2 * sizeof(double)));
+        CU(cudaMalloc(&h->d_trk_out, (size_t)kTrackMaxChannels * kTrackMaxTaps * 2 * sizeof(double)));
+        CU(cudaMalloc(&h->d_trk_mean, (size_t)kTrackMaxChannels * 2 * sizeof(double)));
+        CU(cudaMallocHost(&h->h_trk_out, (size_t)kTrackMaxChannels * kTrackMaxTaps * 2 * sizeof(double)));
+        CU(cudaMemcpyAsync(h->d_trk_ca, ca.data(), ca.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));                        // `ca` is a temporary
+    }
+    CU(cudaMemcpyAsync(h->d_trk_raw, if_samples, nbytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->trk_bytes = nbytes;
+    return GNSSACQ_OK;
+}
+
+int gnssacq_correlate(gnssacq_handle* h, int32_t n_channels, const gnssacq_channel* ch, int32_t n_taps,
+                      const double* spacing_chips, double* out_i, double* out_q) {
+    if (!h || !ch || !spacing_chips || !out_i || !out_q) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (!h->d_trk_raw || !h->trk_bytes) return fail(h, GNSSACQ_ERR_STATE, "gnssacq_track_load first");
+    if (n_channels < 1 || n_channels > kTrackMaxChannels || n_taps < 1 || n_taps > kTrackMaxTaps)
+        return fail(h, GNSSACQ_ERR_INVALID_ARG, "1..64 channels, 1..32 taps");
+    const gnssacq_config& c = h->cfg;
+    const size_t bps = (size_t)c.data_type * c.data_precision;
+    for (int i = 0; i < n_channels; ++i) {
+        if (ch[i].prn < 1 || ch[i].prn > GNSSACQ_TRACK_MAX_PRN) return fail(h, GNSSACQ_ERR_INVALID_ARG, "PRN out of range");
+        if (ch[i].num_samples < 1 || ch[i].sample_offset < 0 ||
+            ((size_t)ch[i].sample_offset + (size_t)ch[i].num_samples) * bps > h->trk_bytes)
+            return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "Not enough raw data (trackingCT.m:107-111)");
+        if (!(ch[i].code_hz > 0.0)) return fail(h, GNSSACQ_ERR_INVALID_ARG, "code_hz must be positive");
+    }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_trk_ch, ch, n_channels * sizeof(gnssacq_channel), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_trk_spacing, spacing_chips, n_taps * sizeof(double), cudaMemcpyHostToDevice, s));
+    TrackArgs a;
+    a.raw = h->d_trk_raw;
+    a.data_type = c.data_type;
+    a.precision = c.data_precision;
+    a.fs_hz = c.fs_hz;
+    a.ch = (const gnssacq_channel*)h->d_trk_ch;
+    a.n_taps = n_taps;
+    a.spacing = h->d_trk_spacing;
+    a.ca = h->d_trk_ca;
+    a.mean = nullptr;
+    a.partial = h->d_trk_partial;
+    if (c.data_precision == 2) {
+        track_mean_kernel<<<n_channels, kTrackThreads, 0, s>>>(a, h->d_trk_mean);
+        a.mean = h->d_trk_mean;
+    }
+    const dim3 grid(kTrackChunks, (unsigned)n_channels, (unsigned)((n_taps + kTrackTapsPerThread - 1) / kTrackTapsPerThread));
+    correlate_kernel<<<grid, kTrackThreads, 0, s>>>(a);
+    const int n_elems = n_channels * n_taps * 2;
+    correlate_finish_kernel<<<(n_elems + 127) / 128, 128, 0, s>>>(h->d_trk_partial, n_taps, n_elems, h->d_trk_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_trk_out, h->d_trk_out, n_elems * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int i = 0; i < n_channels * n_taps; ++i) { out_i[i] = h->h_trk_out[2 * i]; out_q[i] = h->h_trk_out[2 * i + 1]; }
     return GNSSACQ_OK;
 }
 

@@ -56,6 +56,14 @@ class Result(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Channel(C.Structure):
+    """gnssacq_channel: the state of one tracking channel for one integration (trackingCT.m:42-58,78,96,104)."""
+    _fields_ = [
+        ("prn", C.c_int32), ("num_samples", C.c_int32), ("sample_offset", C.c_int64),
+        ("carrier_hz", C.c_double), ("rem_phase", C.c_double), ("code_hz", C.c_double), ("rem_chip", C.c_double),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("wipeoff_fft_ms", C.c_float), ("search_ms", C.c_float),
@@ -74,7 +82,7 @@ EXPORTS = (
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
-    "gnssacq_search_multi", "gnssacq_sweep",
+    "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_track_load", "gnssacq_correlate",
 )
 
 
@@ -105,6 +113,8 @@ def _load() -> C.CDLL:
     lib.gnssacq_fft_forward.argtypes = [vp, vp, vp]
     lib.gnssacq_fine_frequency.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32, vp, vp, vp]
     lib.gnssacq_search_multi.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_size_t, C.POINTER(Result)]
+    lib.gnssacq_track_load.argtypes = [vp, vp, C.c_size_t]
+    lib.gnssacq_correlate.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.c_int32, vp, vp, vp]
     lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
@@ -247,6 +257,21 @@ class Searcher:
         self._check(lib.gnssacq_sweep(self._h, ptrs, n, each, out, C.byref(st)))
         self.last_stats = st
         return [list(out[i * p:(i + 1) * p]) for i in range(n)]
+
+    def track_load(self, if_bytes) -> None:
+        """Keep a segment of the recording resident in HBM for `correlate`."""
+        buf = np.ascontiguousarray(np.frombuffer(if_bytes, dtype=np.uint8) if not isinstance(if_bytes, np.ndarray) else if_bytes)
+        self._check(lib.gnssacq_track_load(self._h, buf.ctypes.data, buf.nbytes))
+
+    def correlate(self, channels: Sequence["Channel"], spacing_chips: Sequence[float]):
+        """One integration period of every channel: (I, Q), each float64 [n_channels, n_taps]."""
+        n, t = len(channels), len(spacing_chips)
+        ch = (Channel * n)(*channels)
+        sp = np.ascontiguousarray(spacing_chips, dtype=np.float64)
+        out_i = np.zeros((n, t), dtype=np.float64)
+        out_q = np.zeros((n, t), dtype=np.float64)
+        self._check(lib.gnssacq_correlate(self._h, n, ch, t, sp.ctypes.data, out_i.ctypes.data, out_q.ctypes.data))
+        return out_i, out_q
 
     def search_device(self, dev_ptr: int, nbytes: int) -> List[Result]:
         out = (Result * self.cfg.n_prn)()

@@ -164,6 +164,29 @@ int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n_handles, const voi
 int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
                   gnssacq_result* out, gnssacq_stats* stats);
 
+/* Tracking correlators (replaces trackingCT.m:85-118, and with 25 taps the correlator bank of
+ * trackingCT_POS_updated_multicorrelator.m:207-260).  The loop filters stay with the caller (trackingCT.m:135-150).
+ * gnssacq_track_load copies a segment of the recording (same sample format as the handle's config) to HBM once;
+ * gnssacq_correlate then runs ONE integration period for a batch of channels against it, in float64:
+ *   carr   = exp(i*(2*pi*carrier_hz*n/Fs + rem_phase)), n = 0..num_samples-1            (:103-106)
+ *   I[tap] = sum(code_tap .* imag(x .* carr)),  Q[tap] = sum(code_tap .* real(x .* carr))  (:112-117)
+ *   code_tap(n) = Code(ceil(spacing[tap] + rem_chip + n*code_hz/Fs) + 1), Code = [CA(end) CA CA(1)]  (:66,96-101)
+ * with x the num_samples samples starting sample_offset samples into the loaded segment (int16 data: the
+ * per-integration means of I and Q are removed, :90-92).  out_i / out_q: [n_channels][n_taps]. */
+#define GNSSACQ_TRACK_MAX_PRN 37
+typedef struct gnssacq_channel {
+    int32_t prn;              /* Acquired.sv(svindex) */
+    int32_t num_samples;      /* numSample (trackingCT.m:78) */
+    int64_t sample_offset;    /* position of the integration in the loaded segment, in samples (ftell/(precision*type)) */
+    double carrier_hz;        /* carrierFreq */
+    double rem_phase;         /* remPhase */
+    double code_hz;           /* codeFreq */
+    double rem_chip;          /* remChip */
+} gnssacq_channel;
+int gnssacq_track_load(gnssacq_handle* h, const void* if_samples, size_t nbytes);
+int gnssacq_correlate(gnssacq_handle* h, int32_t n_channels, const gnssacq_channel* channels, int32_t n_taps,
+                      const double* spacing_chips, double* out_i, double* out_q);
+
 /* Fine-frequency stage (replaces acquisition.m:89-121).  `if_long` is the (L+1) ms block
  * acquisition.m:91/96 reads from the same file offset (host memory); for each of the n_sv acquired SVs
  * (prn[i], code_phase[i] = Acquired.codedelay) the code-stripped L ms are zero-padded to

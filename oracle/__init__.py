@@ -28,4 +28,5 @@ from .acquisition_ref import (  # noqa: F401
     read_if_block,
     CoarseRow,
 )
+from . import tracking_ref  # noqa: F401  (trackingCT.m:75-150, the correlators' oracle)
 from .synth import SynthSpec, SatSpec, synth_if, OPENSKY_TRUTH, URBAN_TRUTH  # noqa: F401

@@ -39,16 +39,17 @@ def test_struct_layout_matches_header():
 #include <stddef.h>
 #include "gnssacq.h"
 int main(void){
- printf("%zu %zu %zu %zu %zu %zu\n", sizeof(gnssacq_config), offsetof(gnssacq_config, prn),
+ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gnssacq_config), offsetof(gnssacq_config, prn),
    offsetof(gnssacq_config, snr_threshold_db), offsetof(gnssacq_config, keep_surface),
-   sizeof(gnssacq_result), sizeof(gnssacq_stats));
+   sizeof(gnssacq_result), sizeof(gnssacq_stats), sizeof(gnssacq_channel), offsetof(gnssacq_channel, carrier_hz));
  return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(probe)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
     want = [C.sizeof(api.Config), api.Config.prn.offset, api.Config.snr_threshold_db.offset,
-            api.Config.keep_surface.offset, C.sizeof(api.Result), C.sizeof(api.Stats)]
+            api.Config.keep_surface.offset, C.sizeof(api.Result), C.sizeof(api.Stats), C.sizeof(api.Channel),
+            api.Channel.carrier_hz.offset]
     assert got == want
 
 
@@ -94,6 +95,8 @@ def test_null_arguments_are_errors_not_crashes():
     assert api.lib.gnssacq_if_bytes(None) == 0
     assert api.lib.gnssacq_search(None, None, 0, None, None) == -1
     assert api.lib.gnssacq_sweep(None, None, 0, 0, None, None) == -1
+    assert api.lib.gnssacq_track_load(None, None, 0) == -1
+    assert api.lib.gnssacq_correlate(None, 0, None, 0, None, None, None) == -1
 
 
 def test_no_cpu_fallback_without_a_device():
