@@ -2,6 +2,10 @@
  *
  *   rows     = gnssacq_mex(raw_int8_or_int16, cfg)                        coarse search
  *   fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay)                 fine-frequency stage
+ *              gnssacq_mex(segment, cfg, 'track_load')                      recording segment -> HBM (tracking)
+ *   [I, Q]   = gnssacq_mex(channels, cfg, spacing, 'correlate')            one integration period, all channels
+ *              channels: 7 x n double, rows [prn; numSample; sample_offset; carrierFreq; remPhase; codeFreq;
+ *              remChip] (trackingCT.m:42-58,78); I, Q: n x numel(spacing) (trackingCT.m:115-117)
  *
  * `raw` is the block acquisition.m:29/34 reads, passed as int8 (or int16) WITHOUT conversion to
  * double; `cfg` is a scalar struct whose fields are named after gnssacq_config.  Returns an
@@ -14,6 +18,7 @@
  * file is compile-checked against tests/stubs/mex.h only.  Build on a MATLAB host with
  *   mex -I<repo>/include gnssacq_mex.c -L<repo>/assignment-for-aae6102_gnss-sdr_b200/gnssacq -lgnssacq
  */
+#include <stdint.h>
 #include <string.h>
 #include "mex.h"
 #include "gnssacq.h"
@@ -45,9 +50,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     double* out;
     int rc, i;
 
-    if ((nrhs != 2 && nrhs != 5) || !mxIsStruct(prhs[1]))
-        fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg) | fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay)");
-    if (!(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
+    if (nrhs < 2 || nrhs > 5 || !mxIsStruct(prhs[1]))
+        fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg) | fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay) | "
+                                      "gnssacq_mex(segment, cfg, 'track_load') | [I, Q] = gnssacq_mex(channels, cfg, spacing, 'correlate')");
+    if (nrhs != 4 && !(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
 
     gnssacq_config_default(&c);
     c.fs_hz = field(prhs[1], "fs_hz", c.fs_hz);
@@ -82,6 +88,43 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     }
 
     nbytes = mxGetNumberOfElements(prhs[0]) * mxGetElementSize(prhs[0]);
+    if (nrhs == 3) {                                   /* tracking: keep the segment in HBM */
+        rc = gnssacq_track_load(g_handle, mxGetData(prhs[0]), nbytes);
+        if (rc != GNSSACQ_OK) fail(rc, gnssacq_last_error(g_handle));
+        return;
+    }
+    if (nrhs == 4) {                                   /* tracking correlators (trackingCT.m:85-118) */
+        const double* m = mxGetPr(prhs[0]);
+        const int n_ch = (int)mxGetN(prhs[0]), n_taps = (int)mxGetNumberOfElements(prhs[2]);
+        gnssacq_channel* ch;
+        double *oi, *oq, *pi, *pq;
+        int t;
+        if (!mxIsDouble(prhs[0]) || mxGetM(prhs[0]) != 7) fail(GNSSACQ_ERR_INVALID_ARG, "channels must be a 7 x n double matrix");
+        ch = (gnssacq_channel*)mxMalloc(sizeof(gnssacq_channel) * (size_t)(n_ch + 1));
+        oi = (double*)mxMalloc(sizeof(double) * (size_t)(n_ch * n_taps + 1));
+        oq = (double*)mxMalloc(sizeof(double) * (size_t)(n_ch * n_taps + 1));
+        for (i = 0; i < n_ch; ++i) {
+            ch[i].prn = (int32_t)m[7 * i];
+            ch[i].num_samples = (int32_t)m[7 * i + 1];
+            ch[i].sample_offset = (int64_t)m[7 * i + 2];
+            ch[i].carrier_hz = m[7 * i + 3];
+            ch[i].rem_phase = m[7 * i + 4];
+            ch[i].code_hz = m[7 * i + 5];
+            ch[i].rem_chip = m[7 * i + 6];
+        }
+        rc = gnssacq_correlate(g_handle, n_ch, ch, n_taps, mxGetPr(prhs[2]), oi, oq);
+        if (rc != GNSSACQ_OK) { mxFree(ch); mxFree(oi); mxFree(oq); fail(rc, gnssacq_last_error(g_handle)); }
+        plhs[0] = mxCreateDoubleMatrix((mwSize)n_ch, (mwSize)n_taps, mxREAL);
+        pi = mxGetPr(plhs[0]);
+        if (nlhs > 1) { plhs[1] = mxCreateDoubleMatrix((mwSize)n_ch, (mwSize)n_taps, mxREAL); pq = mxGetPr(plhs[1]); } else pq = NULL;
+        for (i = 0; i < n_ch; ++i)
+            for (t = 0; t < n_taps; ++t) {             /* row-major [channel][tap] -> MATLAB column-major */
+                pi[i + t * n_ch] = oi[i * n_taps + t];
+                if (pq) pq[i + t * n_ch] = oq[i * n_taps + t];
+            }
+        mxFree(ch); mxFree(oi); mxFree(oq);
+        return;
+    }
     if (nrhs == 5) {                                   /* fine-frequency stage (acquisition.m:83-127) */
         int n_sv = (int)mxGetNumberOfElements(prhs[3]);
         const double* svd = mxGetPr(prhs[3]);

@@ -7,7 +7,8 @@
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
-int mxIsStruct(const mxArray*); int mxIsInt8(const mxArray*); int mxIsInt16(const mxArray*);
+int mxIsStruct(const mxArray*); int mxIsInt8(const mxArray*); int mxIsInt16(const mxArray*); int mxIsDouble(const mxArray*);
+size_t mxGetM(const mxArray*); size_t mxGetN(const mxArray*);
 mxArray* mxGetField(const mxArray*, mwSize, const char*);
 size_t mxGetNumberOfElements(const mxArray*); size_t mxGetElementSize(const mxArray*);
 double mxGetScalar(const mxArray*); double* mxGetPr(const mxArray*); void* mxGetData(const mxArray*);
