@@ -14,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <cooperative_groups.h>
 
 #include "../../include/gnssacq.h"
 #include "gnss_internal.h"
@@ -314,6 +315,147 @@ __global__ void correlate_finish_kernel(const double* __restrict__ partial, int 
     out[e] = v;
 }
 
+// trackingCT.m:70-172 closed on the device.  One cluster of kLoopCtas CTAs per channel; every thread carries an
+// identical copy of the channel state (all updates are the same float64 instruction sequence on the same
+// reduced sums), so one cluster barrier per period is the only synchronisation: per-CTA sums go to a
+// double-buffered shared-memory slot, the barrier publishes them, every CTA adds the slots in rank order.
+constexpr int kLoopCtas = 8, kLoopThreads = 512;
+
+struct LoopArgs {
+    const void* raw;
+    long long total_samples;
+    int data_type, precision;
+    double fs_hz, code_basis_hz;
+    const gnssacq_channel* start;
+    const int8_t* ca;
+    gnssacq_loop_params lp;
+    int n_periods;
+    gnssacq_track_record* out;
+    int* status;              // != 0: some channel ran out of samples
+};
+
+__device__ __forceinline__ double round_half_away(double v) { return v < 0.0 ? -floor(-v + 0.5) : floor(v + 0.5); }
+
+__global__ void __launch_bounds__(kLoopThreads, 1) track_loop_kernel(LoopArgs a) {
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    __shared__ double slot[2][8];                       // [parity][E_i E_q P_i P_q L_i L_q sumI sumQ]
+    __shared__ double wsum[kLoopThreads / 32][8];
+    const int rank = (int)cluster.block_rank(), cidx = blockIdx.x / kLoopCtas;
+    const int gtid = rank * kLoopThreads + threadIdx.x, gthreads = kLoopCtas * kLoopThreads;
+    const gnssacq_channel c0 = a.start[cidx];
+    const int8_t* ca = a.ca + (size_t)(c0.prn - 1) * 1023;
+    // calcLoopCoef.m:41-45
+    const double wn_c = a.lp.dll_bw * 8 * a.lp.dll_damp / (4 * a.lp.dll_damp * a.lp.dll_damp + 1);
+    const double tau1c = a.lp.dll_gain / (wn_c * wn_c), tau2c = 2.0 * a.lp.dll_damp / wn_c;
+    const double wn_p = a.lp.pll_bw * 8 * a.lp.pll_damp / (4 * a.lp.pll_damp * a.lp.pll_damp + 1);
+    const double tau1p = a.lp.pll_gain / (wn_p * wn_p), tau2p = 2.0 * a.lp.pll_damp / wn_p;
+    const double sp[3] = {-a.lp.spacing_chips, 0.0, a.lp.spacing_chips};              // :24
+    double rem_chip = c0.rem_chip, rem_phase = c0.rem_phase, code_hz = c0.code_hz, carrier_hz = c0.carrier_hz;
+    const double carrier_basis = c0.carrier_hz;
+    double code_out_last = 0.0, dll_last = 0.0, carr_out_last = 0.0, pll_last = 0.0;
+    long long pos = c0.sample_offset;
+    const double two_pi = 2.0 * 3.14159265358979323846;
+
+    for (int period = 0; period < a.n_periods; ++period) {
+        const int par = period & 1;
+        const double step = code_hz / a.fs_hz;
+        const int ns = (int)round_half_away((1023.0 - rem_chip) / step);              // :78 (pdi = 1)
+        if (ns < 1 || pos + ns > a.total_samples) {                                   // :107-111 (uniform over the cluster)
+            if (gtid == 0) atomicExch(a.status, 1);
+            break;
+        }
+        double mi = 0.0, mq = 0.0;
+        if (a.precision == 2) {                                                       // :90-92 per-period DC of I and Q
+            const int16_t* p = (const int16_t*)a.raw + 2 * pos;
+            long long si = 0, sq = 0;
+            for (int n = gtid; n < ns; n += gthreads) { si += p[2 * n]; sq += p[2 * n + 1]; }
+            for (int o = 16; o; o >>= 1) { si += __shfl_down_sync(0xffffffffu, si, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+            if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5][6] = (double)si; wsum[threadIdx.x >> 5][7] = (double)sq; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double ti = 0.0, tq = 0.0;                                            // exact: integer-valued, < 2^53
+                for (int w = 0; w < kLoopThreads / 32; ++w) { ti += wsum[w][6]; tq += wsum[w][7]; }
+                slot[par][6] = ti; slot[par][7] = tq;
+            }
+            cluster.sync();
+            double ti = 0.0, tq = 0.0;
+            for (int r = 0; r < kLoopCtas; ++r) {
+                const double* o = cluster.map_shared_rank(&slot[par][0], r);
+                ti += o[6]; tq += o[7];
+            }
+            mi = ti / (double)ns; mq = tq / (double)ns;
+            cluster.sync();                                                           // slots free for the correlator sums
+        }
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const double off0 = (0.0 + sp[0]) + rem_chip, off1 = (0.0 + sp[1]) + rem_chip, off2 = (0.0 + sp[2]) + rem_chip;
+        for (int n = gtid; n < ns; n += gthreads) {
+            double xr, xi;
+            const long long idx = pos + n;
+            if (a.precision == 2) { const int16_t* p = (const int16_t*)a.raw; xr = (double)p[2 * idx] - mi; xi = (double)p[2 * idx + 1] - mq; }
+            else if (a.data_type == 2) { const char2 v = ((const char2*)a.raw)[idx]; xr = (double)v.x; xi = (double)v.y; }
+            else { xr = (double)((const int8_t*)a.raw)[idx]; xi = 0.0; }
+            const double wave = __dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)n / a.fs_hz)), rem_phase);   // :103-104
+            double sn, cs;
+            sincos(wave, &sn, &cs);
+            const double inph = xr * sn + xi * cs, quad = xr * cs - xi * sn;          // :112-113
+            const double sn_d = __dmul_rn(step, (double)n);
+            const double offs[3] = {off0, off1, off2};
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                long long k = (long long)ceil(__dadd_rn(offs[t], sn_d)) - 1;          // :96-101
+                k %= 1023;
+                if (k < 0) k += 1023;
+                const double chip = (double)ca[k];
+                acc[2 * t] += chip * inph;
+                acc[2 * t + 1] += chip * quad;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            for (int o = 16; o; o >>= 1) acc[t] += __shfl_down_sync(0xffffffffu, acc[t], o);
+            if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = acc[t];
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            double v = 0.0;
+            for (int w = 0; w < kLoopThreads / 32; ++w) v += wsum[w][threadIdx.x];
+            slot[par][threadIdx.x] = v;
+        }
+        cluster.sync();                                                               // release/acquire: all slots visible
+        double tot[6] = {0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < kLoopCtas; ++r) {
+            const double* o = cluster.map_shared_rank(&slot[par][0], r);
+#pragma unroll
+            for (int t = 0; t < 6; ++t) tot[t] += o[t];
+        }
+        const double E_i = tot[0], E_q = tot[1], P_i = tot[2], P_q = tot[3], L_i = tot[4], L_q = tot[5];
+        // :102, :105 (with this period's NCO values), then the loops :135-150
+        rem_chip = __dadd_rn(__dadd_rn(__dadd_rn(off1, __dmul_rn(step, (double)(ns - 1))), step), -__dmul_rn(a.code_basis_hz, 1e-3));
+        rem_phase = fmod(__dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)ns / a.fs_hz)), rem_phase), two_pi);
+        pos += ns;
+        const double E = sqrt(E_i * E_i + E_q * E_q), L = sqrt(L_i * L_i + L_q * L_q);
+        const double dll = 0.5 * (E - L) / (E + L);
+        const double code_out = code_out_last + (tau2c / tau1c) * (dll - dll_last) + dll * (0.001 / tau1c);
+        dll_last = dll; code_out_last = code_out;
+        code_hz = a.code_basis_hz - code_out;
+        const double pll = atan(P_q / P_i) / two_pi;
+        const double carr_out = carr_out_last + (tau2p / tau1p) * (pll - pll_last) + pll * (0.001 / tau1p);
+        carr_out_last = carr_out; pll_last = pll;
+        carrier_hz = carrier_basis + carr_out;
+        if (gtid == 0) {
+            gnssacq_track_record r;
+            r.P_i = P_i; r.P_q = P_q; r.E_i = E_i; r.E_q = E_q; r.L_i = L_i; r.L_q = L_q;
+            r.pll_discri = pll; r.dll_discri = dll;
+            r.rem_chip = rem_chip; r.code_hz = code_hz; r.carrier_hz = carrier_hz; r.rem_phase = rem_phase;
+            r.sample_end = pos; r.num_samples = ns; r.reserved = 0;
+            a.out[(size_t)cidx * a.n_periods + period] = r;
+        }
+        // (the next period writes slot[par ^ 1]; slot[par] is rewritten two barriers from now)
+    }
+    cluster.sync();                                        // nobody exits while its slots may still be read
+}
+
 // ---------------------------------------------------------------- handle
 struct gnssacq_handle {
     gnssacq_config cfg;
@@ -370,6 +512,9 @@ struct gnssacq_handle {
     double* d_trk_out = nullptr;           // [channels][taps][2]
     double* d_trk_mean = nullptr;          // [channels][2] int16 path
     double* h_trk_out = nullptr;           // pinned
+    gnssacq_track_record* d_trk_rec = nullptr;   // [channels][periods] of the last gnssacq_track
+    size_t trk_rec_cap = 0;
+    int* d_trk_status = nullptr;
     // pinned host
     void* h_if = nullptr;
     gnssacq_result* h_res = nullptr;
@@ -514,7 +659,7 @@ int gnssacq_destroy(gnssacq_handle* h) {
     for (auto& e : h->ev_consumed) if (e) cudaEventDestroy(e);
     cudaFree(h->d_sums); cudaFree(h->d_means);
     cudaFree(h->d_trk_raw); cudaFree(h->d_trk_ca); cudaFree(h->d_trk_ch); cudaFree(h->d_trk_spacing); cudaFree(h->d_trk_partial);
-    cudaFree(h->d_trk_out); cudaFree(h->d_trk_mean);
+    cudaFree(h->d_trk_out); cudaFree(h->d_trk_mean); cudaFree(h->d_trk_rec); cudaFree(h->d_trk_status);
     if (h->h_trk_out) cudaFreeHost(h->h_trk_out);
     cudaFree(h->d_fft_in); cudaFree(h->d_fft_out);
     cudaFree(h->d_fine_raw); cudaFree(h->d_fine_chip); cudaFree(h->d_fine_u); cudaFree(h->d_fine_ca); cudaFree(h->d_fine_start); cudaFree(h->d_fine_best);
@@ -955,6 +1100,80 @@ int gnssacq_correlate(gnssacq_handle* h, int32_t n_channels, const gnssacq_chann
     CU(cudaMemcpyAsync(h->h_trk_out, h->d_trk_out, n_elems * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     for (int i = 0; i < n_channels * n_taps; ++i) { out_i[i] = h->h_trk_out[2 * i]; out_q[i] = h->h_trk_out[2 * i + 1]; }
+    return GNSSACQ_OK;
+}
+
+int gnssacq_loop_params_default(gnssacq_loop_params* p) {
+    if (!p) return GNSSACQ_ERR_INVALID_ARG;
+    p->dll_bw = 2.0; p->dll_damp = 0.707; p->dll_gain = 0.1;        // initParameters.m:60-62
+    p->pll_bw = 15.0; p->pll_damp = 0.707; p->pll_gain = 0.25;      // initParameters.m:63-65
+    p->spacing_chips = 0.5;                                          // initParameters.m:59
+    return GNSSACQ_OK;
+}
+
+int gnssacq_track(gnssacq_handle* h, int32_t n_channels, const gnssacq_channel* start, const gnssacq_loop_params* loops,
+                  int32_t n_periods, gnssacq_track_record* out) {
+    if (!h || !start || !loops || !out) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (!h->d_trk_raw || !h->trk_bytes) return fail(h, GNSSACQ_ERR_STATE, "gnssacq_track_load first");
+    if (n_channels < 1 || n_channels > kTrackMaxChannels || n_periods < 1)
+        return fail(h, GNSSACQ_ERR_INVALID_ARG, "1..64 channels, at least one period");
+    if (!(loops->dll_bw > 0 && loops->dll_damp > 0 && loops->dll_gain > 0 && loops->pll_bw > 0 && loops->pll_damp > 0 &&
+          loops->pll_gain > 0 && loops->spacing_chips > 0 && loops->spacing_chips < 1.0))
+        return fail(h, GNSSACQ_ERR_INVALID_ARG, "loop parameters must be positive, spacing inside one chip");
+    const gnssacq_config& c = h->cfg;
+    const size_t bps = (size_t)c.data_type * c.data_precision;
+    const long long total = (long long)(h->trk_bytes / bps);
+    for (int i = 0; i < n_channels; ++i) {
+        if (start[i].prn < 1 || start[i].prn > GNSSACQ_TRACK_MAX_PRN) return fail(h, GNSSACQ_ERR_INVALID_ARG, "PRN out of range");
+        if (start[i].sample_offset < 0 || start[i].sample_offset >= total) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "channel starts outside the loaded segment");
+        if (!(start[i].code_hz > 0.0)) return fail(h, GNSSACQ_ERR_INVALID_ARG, "code_hz must be positive");
+    }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t n_rec = (size_t)n_channels * n_periods;
+    if (h->trk_rec_cap < n_rec) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(h->d_trk_rec);
+        h->d_trk_rec = nullptr;
+        h->trk_rec_cap = 0;
+        CU(cudaMalloc(&h->d_trk_rec, n_rec * sizeof(gnssacq_track_record)));
+        h->trk_rec_cap = n_rec;
+    }
+    if (!h->d_trk_status) CU(cudaMalloc(&h->d_trk_status, sizeof(int)));
+    CU(cudaMemsetAsync(h->d_trk_status, 0, sizeof(int), s));
+    CU(cudaMemsetAsync(h->d_trk_rec, 0, n_rec * sizeof(gnssacq_track_record), s));
+    CU(cudaMemcpyAsync(h->d_trk_ch, start, n_channels * sizeof(gnssacq_channel), cudaMemcpyHostToDevice, s));
+    LoopArgs a;
+    a.raw = h->d_trk_raw;
+    a.total_samples = total;
+    a.data_type = c.data_type;
+    a.precision = c.data_precision;
+    a.fs_hz = c.fs_hz;
+    a.code_basis_hz = c.code_hz;
+    a.start = (const gnssacq_channel*)h->d_trk_ch;
+    a.ca = h->d_trk_ca;
+    a.lp = *loops;
+    a.n_periods = n_periods;
+    a.out = h->d_trk_rec;
+    a.status = h->d_trk_status;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(n_channels * kLoopCtas), 1, 1);
+    lc.blockDim = dim3(kLoopThreads, 1, 1);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kLoopCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&lc, track_loop_kernel, a));
+    int status = 0;
+    CU(cudaMemcpyAsync(out, h->d_trk_rec, n_rec * sizeof(gnssacq_track_record), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&status, h->d_trk_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (status) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "Not enough raw data (trackingCT.m:107-111): a channel ran past the loaded segment");
     return GNSSACQ_OK;
 }
 

@@ -64,6 +64,21 @@ class Channel(C.Structure):
     ]
 
 
+class LoopParams(C.Structure):
+    """gnssacq_loop_params: track.DLL*/PLL*/CorrelatorSpacing (initParameters.m:59-65)."""
+    _fields_ = [("dll_bw", C.c_double), ("dll_damp", C.c_double), ("dll_gain", C.c_double),
+                ("pll_bw", C.c_double), ("pll_damp", C.c_double), ("pll_gain", C.c_double),
+                ("spacing_chips", C.c_double)]
+
+
+class TrackRecord(C.Structure):
+    """gnssacq_track_record: the TckResultCT fields of one integration period (trackingCT.m:153-172)."""
+    _fields_ = [("P_i", C.c_double), ("P_q", C.c_double), ("E_i", C.c_double), ("E_q", C.c_double),
+                ("L_i", C.c_double), ("L_q", C.c_double), ("pll_discri", C.c_double), ("dll_discri", C.c_double),
+                ("rem_chip", C.c_double), ("code_hz", C.c_double), ("carrier_hz", C.c_double), ("rem_phase", C.c_double),
+                ("sample_end", C.c_int64), ("num_samples", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("wipeoff_fft_ms", C.c_float), ("search_ms", C.c_float),
@@ -83,6 +98,7 @@ EXPORTS = (
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
     "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_track_load", "gnssacq_correlate",
+    "gnssacq_loop_params_default", "gnssacq_track",
 )
 
 
@@ -114,6 +130,8 @@ def _load() -> C.CDLL:
     lib.gnssacq_fine_frequency.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32, vp, vp, vp]
     lib.gnssacq_search_multi.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_size_t, C.POINTER(Result)]
     lib.gnssacq_track_load.argtypes = [vp, vp, C.c_size_t]
+    lib.gnssacq_loop_params_default.argtypes = [C.POINTER(LoopParams)]
+    lib.gnssacq_track.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.POINTER(LoopParams), C.c_int32, C.POINTER(TrackRecord)]
     lib.gnssacq_correlate.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.c_int32, vp, vp, vp]
     lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
@@ -272,6 +290,17 @@ class Searcher:
         out_q = np.zeros((n, t), dtype=np.float64)
         self._check(lib.gnssacq_correlate(self._h, n, ch, t, sp.ctypes.data, out_i.ctypes.data, out_q.ctypes.data))
         return out_i, out_q
+
+    def track(self, start: Sequence["Channel"], n_periods: int, loops: Optional["LoopParams"] = None) -> List[List["TrackRecord"]]:
+        """trackingCT.m:70-172 on the device: n_periods integration periods per channel, loops closed on the GPU."""
+        if loops is None:
+            loops = LoopParams()
+            lib.gnssacq_loop_params_default(C.byref(loops))
+        n = len(start)
+        ch = (Channel * n)(*start)
+        out = (TrackRecord * (n * n_periods))()
+        self._check(lib.gnssacq_track(self._h, n, ch, C.byref(loops), n_periods, out))
+        return [list(out[i * n_periods:(i + 1) * n_periods]) for i in range(n)]
 
     def search_device(self, dev_ptr: int, nbytes: int) -> List[Result]:
         out = (Result * self.cfg.n_prn)()

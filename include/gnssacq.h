@@ -187,6 +187,30 @@ int gnssacq_track_load(gnssacq_handle* h, const void* if_samples, size_t nbytes)
 int gnssacq_correlate(gnssacq_handle* h, int32_t n_channels, const gnssacq_channel* channels, int32_t n_taps,
                       const double* spacing_chips, double* out_i, double* out_q);
 
+/* The whole conventional tracking loop of trackingCT.m:70-172 on the device: n_periods integration periods of every
+ * channel against the loaded segment, early/prompt/late correlators, DLL and PLL discriminators and loop filters
+ * (calcLoopCoef.m:41-45, trackingCT.m:135-150) in float64, one thread-block cluster per channel, no host round
+ * trip per millisecond.  start[c]: prn, sample_offset = Sample - AcqCodeDelay + 1 (+ skip*Sample) (trackingCT.m:60),
+ * carrier_hz = Acquired.fineFreq (also the NCO basis), code_hz = codeFreqBasis, rem_chip = rem_phase = 0
+ * (num_samples is ignored).  out[c*n_periods + i] holds the TckResultCT fields of period i (trackingCT.m:153-172).
+ * Running out of samples ("Not enough raw data", :107-111) returns GNSSACQ_ERR_SHORT_BUFFER. */
+typedef struct gnssacq_loop_params {
+    double dll_bw, dll_damp, dll_gain;   /* track.DLLBW, DLLDamp, DLLGain   (initParameters.m:60-62) */
+    double pll_bw, pll_damp, pll_gain;   /* track.PLLBW, PLLDamp, PLLGain   (initParameters.m:63-65) */
+    double spacing_chips;                /* track.CorrelatorSpacing         (initParameters.m:59)    */
+} gnssacq_loop_params;
+typedef struct gnssacq_track_record {
+    double P_i, P_q, E_i, E_q, L_i, L_q;  /* :115-117 */
+    double pll_discri, dll_discri;        /* :146, :139 */
+    double rem_chip, code_hz, carrier_hz, rem_phase;   /* values AFTER the period's update, as stored at :164-167 */
+    int64_t sample_end;                   /* absoluteSample/(dataPrecision*dataType): position after the read (:171) */
+    int32_t num_samples;                  /* :78 */
+    int32_t reserved;
+} gnssacq_track_record;
+int gnssacq_loop_params_default(gnssacq_loop_params* p);
+int gnssacq_track(gnssacq_handle* h, int32_t n_channels, const gnssacq_channel* start, const gnssacq_loop_params* loops,
+                  int32_t n_periods, gnssacq_track_record* out);
+
 /* Fine-frequency stage (replaces acquisition.m:89-121).  `if_long` is the (L+1) ms block
  * acquisition.m:91/96 reads from the same file offset (host memory); for each of the n_sv acquired SVs
  * (prn[i], code_phase[i] = Acquired.codedelay) the code-stripped L ms are zero-padded to

@@ -39,7 +39,8 @@ def test_struct_layout_matches_header():
 #include <stddef.h>
 #include "gnssacq.h"
 int main(void){
- printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gnssacq_config), offsetof(gnssacq_config, prn),
+ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gnssacq_loop_params), sizeof(gnssacq_track_record),
+   offsetof(gnssacq_track_record, num_samples), sizeof(gnssacq_config), offsetof(gnssacq_config, prn),
    offsetof(gnssacq_config, snr_threshold_db), offsetof(gnssacq_config, keep_surface),
    sizeof(gnssacq_result), sizeof(gnssacq_stats), sizeof(gnssacq_channel), offsetof(gnssacq_channel, carrier_hz));
  return 0; }'''
@@ -47,7 +48,7 @@ int main(void){
         open(os.path.join(d, "p.c"), "w").write(probe)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
-    want = [C.sizeof(api.Config), api.Config.prn.offset, api.Config.snr_threshold_db.offset,
+    want = [C.sizeof(api.LoopParams), C.sizeof(api.TrackRecord), api.TrackRecord.num_samples.offset, C.sizeof(api.Config), api.Config.prn.offset, api.Config.snr_threshold_db.offset,
             api.Config.keep_surface.offset, C.sizeof(api.Result), C.sizeof(api.Stats), C.sizeof(api.Channel),
             api.Channel.carrier_hz.offset]
     assert got == want
@@ -97,6 +98,11 @@ def test_null_arguments_are_errors_not_crashes():
     assert api.lib.gnssacq_sweep(None, None, 0, 0, None, None) == -1
     assert api.lib.gnssacq_track_load(None, None, 0) == -1
     assert api.lib.gnssacq_correlate(None, 0, None, 0, None, None, None) == -1
+    assert api.lib.gnssacq_track(None, 0, None, None, 0, None) == -1
+    assert api.lib.gnssacq_loop_params_default(None) == -1
+    lp = api.LoopParams()
+    assert api.lib.gnssacq_loop_params_default(C.byref(lp)) == 0
+    assert (lp.dll_bw, lp.dll_damp, lp.dll_gain, lp.pll_bw, lp.pll_damp, lp.pll_gain, lp.spacing_chips) == (2.0, 0.707, 0.1, 15.0, 0.707, 0.25, 0.5)   # initParameters.m:59-65
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -115,3 +115,45 @@ def test_correlate_argument_errors():
                 s.correlate([b], EPL)
         with pytest.raises(gnssacq.GnssAcqError):
             s.correlate([ch], [0.0] * 33)
+
+
+@pytest.mark.parametrize("fs,if_hz,data_type,precision,periods", [(26e6, 0.0, 2, 1, 60), (58e6, 4.58e6, 2, 1, 25),
+                                                                   (6e6, 1.25e6, 2, 2, 40), (6e6, 1.25e6, 1, 1, 40)])
+def test_device_side_tracking_loop_against_the_oracle_loop(fs, if_hz, data_type, precision, periods):
+    """gnssacq_track: trackingCT.m:70-172 closed on the GPU (one cluster per channel, no host round trip per ms).
+    Period by period against the oracle's loop: numSample and the file position identical, sums to 1e-7 of the
+    prompt magnitude, NCO frequencies to 1e-6 Hz; and the loops lock."""
+    n = int(fs * 1e-3)
+    truth = [(5, 1500.0, (n * 2) // 13, 5.0), (17, -2750.0, (n * 7) // 12, 4.0), (30, 420.0, 11, 6.0)]
+    spec = SynthSpec(fs=fs, if_hz=if_hz, samples_per_ms=n, sigma=6.0, data_type=data_type, data_precision=precision,
+                     seed=5, sats=[SatSpec(p, d, cd, a, 0.4) for p, d, cd, a in truth])
+    raw = synth_if(spec, 0, periods + 3)
+    start = [api.Channel(prn=p, num_samples=0, sample_offset=n - cd + 1, carrier_hz=if_hz + d + 8.0, rem_phase=0.0,
+                         code_hz=1.023e6, rem_chip=0.0) for p, d, cd, a in truth]
+    with api.Searcher(_cfg(fs, if_hz, data_type, precision)) as s:
+        s.track_load(raw)
+        recs = s.track(start, periods)
+        again = s.track(start, periods)
+        assert [bytes(r) for ch in recs for r in ch] == [bytes(r) for ch in again for r in ch]       # deterministic
+        with pytest.raises(gnssacq.GnssAcqError) as e:                                                # :107-111
+            s.track(start, periods + 10)
+        assert e.value.code == -3
+    bps = data_type * precision
+    for c, (p, d, cd, a) in enumerate(truth):
+        st = tr.ChannelState(prn=p, carrier_basis_hz=if_hz + d + 8.0, carrier_hz=if_hz + d + 8.0, sample_pos=n - cd + 1)
+        for i, r in enumerate(recs[c]):
+            ns = tr.num_samples(st.code_hz, fs, st.rem_chip)
+            assert r.num_samples == ns, f"channel {c} period {i}: numSample {r.num_samples} != {ns}"
+            x = tr.samples_of(raw[st.sample_pos * bps:(st.sample_pos + ns) * bps], data_type, precision)
+            oi, oq = tr.correlate(x, fs, p, st.carrier_hz, st.rem_phase, st.code_hz, st.rem_chip, EPL)
+            tr.close_loops(st, oi, oq, ns, fs)
+            scale = max(np.hypot(oi[1], oq[1]), 1.0)
+            got = np.array([r.E_i, r.P_i, r.L_i, r.E_q, r.P_q, r.L_q])
+            assert np.abs(got - np.concatenate([oi, oq])).max() <= 1e-7 * scale, f"channel {c} period {i}"
+            assert r.sample_end == st.sample_pos
+            assert abs(r.code_hz - st.code_hz) <= 1e-6 and abs(r.carrier_hz - st.carrier_hz) <= 1e-6
+            assert abs(r.rem_chip - st.rem_chip) <= 1e-9 and abs(r.rem_phase - st.rem_phase) <= 1e-7
+        tail = recs[c][15:]
+        if data_type == 2:                                   # (a real-sampled signal carries half the power per sideband)
+            assert np.median([np.hypot(r.P_i, r.P_q) for r in tail]) > 0.8 * a * n
+        assert abs(np.mean([r.carrier_hz for r in tail]) - (if_hz + d)) < 15.0
