@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) track_loop_kernel(LoopArgs a)
     cgx::cluster_group cluster = cgx::this_cluster();
     __shared__ double slot[2][8];                       // [parity][E_i E_q P_i P_q L_i L_q sumI sumQ]
     __shared__ double wsum[kLoopThreads / 32][8];
+    __shared__ double total[2][6];                      // cluster-wide sums of the period (same in every CTA)
     const int rank = (int)cluster.block_rank(), cidx = blockIdx.x / kLoopCtas;
     const int gtid = rank * kLoopThreads + threadIdx.x, gthreads = kLoopCtas * kLoopThreads;
     const gnssacq_channel c0 = a.start[cidx];
@@ -351,17 +352,30 @@ __global__ void __launch_bounds__(kLoopThreads, 1) track_loop_kernel(LoopArgs a)
     const double wn_p = a.lp.pll_bw * 8 * a.lp.pll_damp / (4 * a.lp.pll_damp * a.lp.pll_damp + 1);
     const double tau1p = a.lp.pll_gain / (wn_p * wn_p), tau2p = 2.0 * a.lp.pll_damp / wn_p;
     const double sp[3] = {-a.lp.spacing_chips, 0.0, a.lp.spacing_chips};              // :24
-    double rem_chip = c0.rem_chip, rem_phase = c0.rem_phase, code_hz = c0.code_hz, carrier_hz = c0.carrier_hz;
+    // The channel state lives in shared memory; thread 0 of EVERY CTA advances it (the same float64 instruction
+    // sequence on the same sums in all eight CTAs -- identical results, no exchange), the other threads only read
+    // it: the scalar loop math (divisions, sqrt, atan, fmod) would otherwise be executed 4096 times per period.
+    struct State { double rem_chip, rem_phase, code_hz, carrier_hz, step; long long pos; int ns; int stop; };
+    __shared__ State state[2];
     const double carrier_basis = c0.carrier_hz;
-    double code_out_last = 0.0, dll_last = 0.0, carr_out_last = 0.0, pll_last = 0.0;
-    long long pos = c0.sample_offset;
+    double code_out_last = 0.0, dll_last = 0.0, carr_out_last = 0.0, pll_last = 0.0;          // (thread 0 only)
     const double two_pi = 2.0 * 3.14159265358979323846;
+    auto publish = [&](State& st, double rem_chip, double rem_phase, double code_hz, double carrier_hz, long long pos) {
+        st.rem_chip = rem_chip; st.rem_phase = rem_phase; st.code_hz = code_hz; st.carrier_hz = carrier_hz; st.pos = pos;
+        st.step = code_hz / a.fs_hz;
+        st.ns = (int)round_half_away((1023.0 - rem_chip) / st.step);                  // :78 (pdi = 1)
+        st.stop = (st.ns < 1 || pos + st.ns > a.total_samples) ? 1 : 0;               // :107-111
+    };
+    if (threadIdx.x == 0) publish(state[0], c0.rem_chip, c0.rem_phase, c0.code_hz, c0.carrier_hz, c0.sample_offset);
+    __syncthreads();
 
     for (int period = 0; period < a.n_periods; ++period) {
         const int par = period & 1;
-        const double step = code_hz / a.fs_hz;
-        const int ns = (int)round_half_away((1023.0 - rem_chip) / step);              // :78 (pdi = 1)
-        if (ns < 1 || pos + ns > a.total_samples) {                                   // :107-111 (uniform over the cluster)
+        const double rem_chip = state[par].rem_chip, rem_phase = state[par].rem_phase, carrier_hz = state[par].carrier_hz,
+                     code_hz = state[par].code_hz, step = state[par].step;
+        const long long pos = state[par].pos;
+        const int ns = state[par].ns;
+        if (state[par].stop) {                                                        // uniform over the cluster
             if (gtid == 0) atomicExch(a.status, 1);
             break;
         }
@@ -389,26 +403,47 @@ __global__ void __launch_bounds__(kLoopThreads, 1) track_loop_kernel(LoopArgs a)
         }
         double acc[6] = {0, 0, 0, 0, 0, 0};
         const double off0 = (0.0 + sp[0]) + rem_chip, off1 = (0.0 + sp[1]) + rem_chip, off2 = (0.0 + sp[2]) + rem_chip;
-        for (int n = gtid; n < ns; n += gthreads) {
-            double xr, xi;
-            const long long idx = pos + n;
-            if (a.precision == 2) { const int16_t* p = (const int16_t*)a.raw; xr = (double)p[2 * idx] - mi; xi = (double)p[2 * idx + 1] - mq; }
-            else if (a.data_type == 2) { const char2 v = ((const char2*)a.raw)[idx]; xr = (double)v.x; xi = (double)v.y; }
-            else { xr = (double)((const int8_t*)a.raw)[idx]; xi = 0.0; }
-            const double wave = __dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)n / a.fs_hz)), rem_phase);   // :103-104
-            double sn, cs;
-            sincos(wave, &sn, &cs);
-            const double inph = xr * sn + xi * cs, quad = xr * cs - xi * sn;          // :112-113
-            const double sn_d = __dmul_rn(step, (double)n);
-            const double offs[3] = {off0, off1, off2};
+        // Carrier replica (:103-106): this thread's samples are n = gtid + j*gthreads, so its phasor advances by a
+        // constant rotation per step -- two sincos per period instead of one per sample (the rotation's rounding
+        // grows by ~1e-16 per step over <= 15 steps; gnssacq_correlate keeps the per-sample form).
+        double cs, sn, rc, rs;
+        sincos(__dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)gtid / a.fs_hz)), rem_phase), &sn, &cs);
+        sincos(two_pi * (carrier_hz * ((double)gthreads / a.fs_hz)), &rs, &rc);
+        constexpr int kBatch = 16;                       // samples per thread fetched before any is used: the loads
+        for (int n0 = gtid; n0 < ns; n0 += kBatch * gthreads) {          // overlap instead of paying 15 L2/HBM latencies in a row
+            float fr[kBatch], fi[kBatch];                // (int8 / int16 values are exact in float)
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                long long k = (long long)ceil(__dadd_rn(offs[t], sn_d)) - 1;          // :96-101
-                k %= 1023;
-                if (k < 0) k += 1023;
-                const double chip = (double)ca[k];
-                acc[2 * t] += chip * inph;
-                acc[2 * t + 1] += chip * quad;
+            for (int j = 0; j < kBatch; ++j) {
+                const int n = n0 + j * gthreads;
+                fr[j] = fi[j] = 0.f;
+                if (n < ns) {
+                    const long long idx = pos + n;
+                    if (a.precision == 2) { const short2 v = ((const short2*)a.raw)[idx]; fr[j] = (float)v.x; fi[j] = (float)v.y; }
+                    else if (a.data_type == 2) { const char2 v = ((const char2*)a.raw)[idx]; fr[j] = (float)v.x; fi[j] = (float)v.y; }
+                    else fr[j] = (float)((const int8_t*)a.raw)[idx];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int n = n0 + j * gthreads;
+                if (n < ns) {
+                    const double xr = (double)fr[j] - mi, xi = (a.data_type == 2 || a.precision == 2) ? (double)fi[j] - mq : 0.0;
+                    const double inph = xr * sn + xi * cs, quad = xr * cs - xi * sn;          // :112-113
+                    const double cn = cs * rc - sn * rs;
+                    sn = sn * rc + cs * rs;
+                    cs = cn;
+                    const double sn_d = __dmul_rn(step, (double)n);
+                    const double offs[3] = {off0, off1, off2};
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        int k = (int)ceil(__dadd_rn(offs[t], sn_d)) - 1;                      // :96-101; |t| < 2^31 chips by far
+                        k %= 1023;
+                        if (k < 0) k += 1023;
+                        const double chip = (double)ca[k];
+                        acc[2 * t] += chip * inph;
+                        acc[2 * t + 1] += chip * quad;
+                    }
+                }
             }
         }
 #pragma unroll
@@ -423,35 +458,40 @@ __global__ void __launch_bounds__(kLoopThreads, 1) track_loop_kernel(LoopArgs a)
             slot[par][threadIdx.x] = v;
         }
         cluster.sync();                                                               // release/acquire: all slots visible
-        double tot[6] = {0, 0, 0, 0, 0, 0};
-        for (int r = 0; r < kLoopCtas; ++r) {
-            const double* o = cluster.map_shared_rank(&slot[par][0], r);
-#pragma unroll
-            for (int t = 0; t < 6; ++t) tot[t] += o[t];
+        if (threadIdx.x < 6) {                                                        // six threads pull the eight slots
+            double v = 0.0;
+            for (int r = 0; r < kLoopCtas; ++r) v += cluster.map_shared_rank(&slot[par][0], r)[threadIdx.x];
+            total[par][threadIdx.x] = v;
         }
-        const double E_i = tot[0], E_q = tot[1], P_i = tot[2], P_q = tot[3], L_i = tot[4], L_q = tot[5];
-        // :102, :105 (with this period's NCO values), then the loops :135-150
-        rem_chip = __dadd_rn(__dadd_rn(__dadd_rn(off1, __dmul_rn(step, (double)(ns - 1))), step), -__dmul_rn(a.code_basis_hz, 1e-3));
-        rem_phase = fmod(__dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)ns / a.fs_hz)), rem_phase), two_pi);
-        pos += ns;
-        const double E = sqrt(E_i * E_i + E_q * E_q), L = sqrt(L_i * L_i + L_q * L_q);
-        const double dll = 0.5 * (E - L) / (E + L);
-        const double code_out = code_out_last + (tau2c / tau1c) * (dll - dll_last) + dll * (0.001 / tau1c);
-        dll_last = dll; code_out_last = code_out;
-        code_hz = a.code_basis_hz - code_out;
-        const double pll = atan(P_q / P_i) / two_pi;
-        const double carr_out = carr_out_last + (tau2p / tau1p) * (pll - pll_last) + pll * (0.001 / tau1p);
-        carr_out_last = carr_out; pll_last = pll;
-        carrier_hz = carrier_basis + carr_out;
-        if (gtid == 0) {
-            gnssacq_track_record r;
-            r.P_i = P_i; r.P_q = P_q; r.E_i = E_i; r.E_q = E_q; r.L_i = L_i; r.L_q = L_q;
-            r.pll_discri = pll; r.dll_discri = dll;
-            r.rem_chip = rem_chip; r.code_hz = code_hz; r.carrier_hz = carrier_hz; r.rem_phase = rem_phase;
-            r.sample_end = pos; r.num_samples = ns; r.reserved = 0;
-            a.out[(size_t)cidx * a.n_periods + period] = r;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double E_i = total[par][0], E_q = total[par][1], P_i = total[par][2], P_q = total[par][3],
+                         L_i = total[par][4], L_q = total[par][5];
+            // :102, :105 (with this period's NCO values), then the loops :135-150
+            const double n_rem_chip = __dadd_rn(__dadd_rn(__dadd_rn(off1, __dmul_rn(step, (double)(ns - 1))), step), -__dmul_rn(a.code_basis_hz, 1e-3));
+            const double n_rem_phase = fmod(__dadd_rn(__dmul_rn(two_pi, __dmul_rn(carrier_hz, (double)ns / a.fs_hz)), rem_phase), two_pi);
+            const double E = sqrt(E_i * E_i + E_q * E_q), L = sqrt(L_i * L_i + L_q * L_q);
+            const double dll = 0.5 * (E - L) / (E + L);
+            const double code_out = code_out_last + (tau2c / tau1c) * (dll - dll_last) + dll * (0.001 / tau1c);
+            dll_last = dll; code_out_last = code_out;
+            const double n_code_hz = a.code_basis_hz - code_out;
+            const double pll = atan(P_q / P_i) / two_pi;
+            const double carr_out = carr_out_last + (tau2p / tau1p) * (pll - pll_last) + pll * (0.001 / tau1p);
+            carr_out_last = carr_out; pll_last = pll;
+            const double n_carrier_hz = carrier_basis + carr_out;
+            publish(state[par ^ 1], n_rem_chip, n_rem_phase, n_code_hz, n_carrier_hz, pos + ns);
+            if (rank == 0) {
+                gnssacq_track_record r;
+                r.P_i = P_i; r.P_q = P_q; r.E_i = E_i; r.E_q = E_q; r.L_i = L_i; r.L_q = L_q;
+                r.pll_discri = pll; r.dll_discri = dll;
+                r.rem_chip = n_rem_chip; r.code_hz = n_code_hz; r.carrier_hz = n_carrier_hz; r.rem_phase = n_rem_phase;
+                r.sample_end = pos + ns; r.num_samples = ns; r.reserved = 0;
+                a.out[(size_t)cidx * a.n_periods + period] = r;
+            }
         }
-        // (the next period writes slot[par ^ 1]; slot[par] is rewritten two barriers from now)
+        __syncthreads();                                   // state[par ^ 1] is complete
+        // (the next period writes slot[par ^ 1]; slot[par] is rewritten two cluster barriers from now)
+        (void)code_hz;
     }
     cluster.sync();                                        // nobody exits while its slots may still be read
 }

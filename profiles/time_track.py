@@ -9,7 +9,7 @@ from gnssacq import api
 from gnssacq.synth import opensky_recording
 from oracle import tracking_ref as tr
 
-fs, if_hz, n, periods = 58e6, 4.58e6, 58000, 400
+fs, if_hz, n, periods = 58e6, 4.58e6, 58000, 1000
 rec = opensky_recording()
 raw = rec.read(0, periods + 3)
 truth = list(zip((3, 4, 16, 22, 26, 27, 31, 32), (990.0, -3095.0, -305.0, 1565.0, 1835.0, -3225.0, 1045.0, 3345.0),
@@ -19,7 +19,7 @@ start = [api.Channel(prn=t[0], num_samples=0, sample_offset=n - t[2] + 1, carrie
 with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=[1])) as s:
     s.track_load(raw)
     for n_ch in (1, 8):
-        s.track(start[:n_ch], 10)
+        s.track(start[:n_ch], periods)                      # (also sizes the record buffer)
         t0 = time.perf_counter()
         recs = s.track(start[:n_ch], periods)
         dt = time.perf_counter() - t0
