@@ -347,7 +347,8 @@ def run_gpu(args, cfg):
             "config": {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
                        "coh_ms": cfg["m"], "prns": 32, "cells": cells, "cell_blocks": cells * cfg["k"],
                        "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2+clusters", 3: "l2+coop-groups"}.get(st.exchange),
-                                  "resident_clusters": st.resident_clusters},
+                                  "resident_clusters": st.resident_clusters,
+                                  "work_split": {1: "whole rows", 2: "block-granular tail"}.get(st.work_split)},
                        "sharding": f"PRN-major, {n_local} PRNs on rank 0",
                        "l2": "flushed between steps (256 MiB device memset, outside the per-step event pair)",
                        "latency_ms_32prn": e2e_s / args.steps * 1e3,
