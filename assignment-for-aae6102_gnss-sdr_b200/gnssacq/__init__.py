@@ -4,3 +4,4 @@ from .api import Config, Result, Stats, Channel, LoopParams, TrackRecord, Search
 from .acquisition import acquisition, config_from_structs, get_searcher, release_all  # noqa: F401
 from .params import initParameters  # noqa: F401
 from .matfile import save_acquired, load_acquired, acquired_filename, cached_acquisition  # noqa: F401
+from .tracking import trackingCT, trackParameters, cn0_estimates, bit_edge_index  # noqa: F401

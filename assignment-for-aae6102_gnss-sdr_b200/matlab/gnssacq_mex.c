@@ -6,6 +6,10 @@
  *   [I, Q]   = gnssacq_mex(channels, cfg, spacing, 'correlate')            one integration period, all channels
  *              channels: 7 x n double, rows [prn; numSample; sample_offset; carrierFreq; remPhase; codeFreq;
  *              remChip] (trackingCT.m:42-58,78); I, Q: n x numel(spacing) (trackingCT.m:115-117)
+ *   rec      = gnssacq_mex(channels, cfg, loops, n_periods, 'track')       closed DLL/PLL loop on the device
+ *              loops: [DLLBW DLLDamp DLLGain PLLBW PLLDamp PLLGain CorrelatorSpacing]; rec: 14 x n_periods x n,
+ *              rows [P_i P_q E_i E_q L_i L_q PLLdiscri DLLdiscri remChip codeFreq carrierFreq remPhase
+ *              sample_end numSample] (trackingCT.m:153-172)
  *
  * `raw` is the block acquisition.m:29/34 reads, passed as int8 (or int16) WITHOUT conversion to
  * double; `cfg` is a scalar struct whose fields are named after gnssacq_config.  Returns an
@@ -48,12 +52,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     gnssacq_result* rows;
     size_t nbytes;
     double* out;
-    int rc, i;
+    int rc, i, track_mode;
 
     if (nrhs < 2 || nrhs > 5 || !mxIsStruct(prhs[1]))
         fail(GNSSACQ_ERR_INVALID_ARG, "usage: rows = gnssacq_mex(raw, cfg) | fineFreq = gnssacq_mex(longraw, cfg, L, sv, codedelay) | "
                                       "gnssacq_mex(segment, cfg, 'track_load') | [I, Q] = gnssacq_mex(channels, cfg, spacing, 'correlate')");
-    if (nrhs != 4 && !(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
+    track_mode = (nrhs == 5 && mxIsChar(prhs[4]));
+    if (nrhs != 4 && !track_mode && !(mxIsInt8(prhs[0]) || mxIsInt16(prhs[0]))) fail(GNSSACQ_ERR_INVALID_ARG, "raw must be int8 or int16");
 
     gnssacq_config_default(&c);
     c.fs_hz = field(prhs[1], "fs_hz", c.fs_hz);
@@ -123,6 +128,46 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                 if (pq) pq[i + t * n_ch] = oq[i * n_taps + t];
             }
         mxFree(ch); mxFree(oi); mxFree(oq);
+        return;
+    }
+    if (track_mode) {                                  /* whole conventional loop (trackingCT.m:70-172) */
+        const double* m = mxGetPr(prhs[0]);
+        const double* lp = mxGetPr(prhs[2]);
+        const int n_ch = (int)mxGetN(prhs[0]), n_per = (int)mxGetScalar(prhs[3]);
+        gnssacq_channel* ch;
+        gnssacq_track_record* rec;
+        gnssacq_loop_params loops;
+        mwSize dims[3];
+        int k;
+        if (!mxIsDouble(prhs[0]) || mxGetM(prhs[0]) != 7 || mxGetNumberOfElements(prhs[2]) != 7 || n_per < 1)
+            fail(GNSSACQ_ERR_INVALID_ARG, "track: channels 7 x n, loops 1 x 7, n_periods >= 1");
+        loops.dll_bw = lp[0]; loops.dll_damp = lp[1]; loops.dll_gain = lp[2];
+        loops.pll_bw = lp[3]; loops.pll_damp = lp[4]; loops.pll_gain = lp[5]; loops.spacing_chips = lp[6];
+        ch = (gnssacq_channel*)mxMalloc(sizeof(gnssacq_channel) * (size_t)(n_ch + 1));
+        rec = (gnssacq_track_record*)mxMalloc(sizeof(gnssacq_track_record) * ((size_t)n_ch * (size_t)n_per + 1));
+        for (i = 0; i < n_ch; ++i) {
+            ch[i].prn = (int32_t)m[7 * i];
+            ch[i].num_samples = 0;
+            ch[i].sample_offset = (int64_t)m[7 * i + 2];
+            ch[i].carrier_hz = m[7 * i + 3];
+            ch[i].rem_phase = m[7 * i + 4];
+            ch[i].code_hz = m[7 * i + 5];
+            ch[i].rem_chip = m[7 * i + 6];
+        }
+        rc = gnssacq_track(g_handle, n_ch, ch, &loops, n_per, rec);
+        if (rc != GNSSACQ_OK) { mxFree(ch); mxFree(rec); fail(rc, gnssacq_last_error(g_handle)); }
+        dims[0] = 14; dims[1] = (mwSize)n_per; dims[2] = (mwSize)n_ch;
+        plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        out = mxGetPr(plhs[0]);
+        for (i = 0; i < n_ch; ++i)
+            for (k = 0; k < n_per; ++k) {
+                const gnssacq_track_record* r = &rec[(size_t)i * n_per + k];
+                double* o = out + 14 * ((size_t)i * n_per + k);
+                o[0] = r->P_i; o[1] = r->P_q; o[2] = r->E_i; o[3] = r->E_q; o[4] = r->L_i; o[5] = r->L_q;
+                o[6] = r->pll_discri; o[7] = r->dll_discri; o[8] = r->rem_chip; o[9] = r->code_hz;
+                o[10] = r->carrier_hz; o[11] = r->rem_phase; o[12] = (double)r->sample_end; o[13] = r->num_samples;
+            }
+        mxFree(ch); mxFree(rec);
         return;
     }
     if (nrhs == 5) {                                   /* fine-frequency stage (acquisition.m:83-127) */

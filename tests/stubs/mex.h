@@ -7,6 +7,9 @@
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
+typedef enum { mxDOUBLE_CLASS = 6 } mxClassID;
+int mxIsChar(const mxArray*);
+mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 int mxIsStruct(const mxArray*); int mxIsInt8(const mxArray*); int mxIsInt16(const mxArray*); int mxIsDouble(const mxArray*);
 size_t mxGetM(const mxArray*); size_t mxGetN(const mxArray*);
 mxArray* mxGetField(const mxArray*, mwSize, const char*);

@@ -157,3 +157,47 @@ def test_device_side_tracking_loop_against_the_oracle_loop(fs, if_hz, data_type,
         if data_type == 2:                                   # (a real-sampled signal carries half the power per sideband)
             assert np.median([np.hypot(r.P_i, r.P_q) for r in tail]) > 0.8 * a * n
         assert abs(np.mean([r.carrier_hz for r in tail]) - (if_hz + d)) < 15.0
+
+
+def test_trackingct_twin_on_a_synthetic_recording():
+    """gnssacq.trackingCT (stage 1 of trackingCT.m) on a synthetic 6 MHz recording: locks on every acquired SV, the
+    per-period fields have the reference's meaning, C/N0 matches the generator's signal and noise levels, and the
+    bit-edge index points at the generator's 20 ms data-bit grid."""
+    from oracle.synth import VirtualFile
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    truth = [(3, 990.0, 4800, 5.0), (22, -2310.0, 5100, 6.0)]          # code delays near N: bit edges late in a period
+    sigma = 5.0
+    spec = SynthSpec(fs=fs, if_hz=if_hz, samples_per_ms=n, sigma=sigma, data_type=2, data_precision=1, seed=77,
+                     sats=[SatSpec(p, d, cd, a, 0.2) for p, d, cd, a in truth])
+    file, signal, acq = structs(fs, if_hz, datalen=2, skip=3)
+    file.fid = VirtualFile(spec)
+    signal.ms, signal.Sample = 1e-3, n
+    track = gnssacq.trackParameters()
+    track.msToProcessCT_1ms = 700
+    acquired = {"sv": np.array([p for p, *_ in truth], float), "codedelay": np.array([cd for _, _, cd, _ in truth], float),
+                "fineFreq": np.array([if_hz + d + 6.0 for _, d, _, _ in truth])}
+    res, cn0, countinx = gnssacq.trackingCT(file, signal, track, acquired)
+    gnssacq.release_all()
+    assert sorted(res) == [3, 22] and cn0.shape == (35, 2) and countinx.shape == (2,)
+    for c, (p, d, cd, a) in enumerate(truth):
+        r = res[p]
+        assert all(len(r[k]) == 700 for k in r)
+        pw = np.hypot(r["P_i"][50:], r["P_q"][50:])
+        assert np.median(pw) > 0.85 * a * n
+        assert abs(np.mean(r["carrierFreq"][100:]) - (if_hz + d)) < 5.0
+        assert abs(np.mean(r["codeFreq"][100:]) - 1.023e6) < 2.0          # (the generator has no code Doppler)
+        assert np.all(np.abs(r["delayValue"]) <= 1) and np.all(r["numSample"] == n + r["delayValue"])
+        assert np.allclose(r["codedelay"], cd + np.cumsum(r["delayValue"]))
+        bps = 2
+        assert r["absoluteSample"][0] == ((3 * n) + (n - cd + 1) + r["numSample"][0]) * bps       # ftell after the first read
+        # C/N0 (trackingCT.m:121-133): the formula itself is pinned on the CPU (tests/test_tracking_host.py); here
+        # the wiring -- 35 blocks of 20 periods from this channel's prompt sums.  (At 6 samples per chip the +-1
+        # sample code-phase steps modulate |P| by a few per cent, which caps what the moment method reports far
+        # below the generator's 65 dB-Hz.)
+        assert np.array_equal(cn0[:, c], gnssacq.cn0_estimates(r["P_i"], r["P_q"]))
+        assert 40.0 < np.nanmedian(cn0[:, c]) < 70.0
+        # the generator flips data bits on file-ms multiples of 20: (cd - 1) samples into tracking period 20m - 3
+        # (skip = 3 ms), so the first fully flipped period is 20m - 2 (1-based) and countinx = mod(i, 20) - 1 = 17,
+        # unless no bit flipped between periods 600 and 682 (then 0)
+        assert countinx[c] in (17.0, 0.0)
+    assert (countinx == 17.0).any()
