@@ -389,3 +389,35 @@ def test_reacquisition_sweep_equals_single_searches(n, datalen, n_windows):
         with pytest.raises(gnssacq.GnssAcqError):
             s.sweep([windows[0][:-2]])
     assert_rows_match(swept[0], oracle_rows(windows[0], file, signal, acq, prns), what=f"sweep N={n} window 0")
+
+
+def test_plain_c_example_end_to_end(tmp_path):
+    """examples/acquire.c -- the ABI from plain C, no Python in the process: acquire a synthetic Opensky-shaped
+    recording from a file and print acquisition.m's lines; the numbers must be the ones the ctypes path gets."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "assignment-for-aae6102_gnss-sdr_b200", "gnssacq")
+    exe = str(tmp_path / "acquire")
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "acquire.c"),
+                           "-L", pkg, "-lgnssacq", "-o", exe])
+    spec = opensky_spec()
+    raw = synth_if(spec, 0, 21)
+    rec = tmp_path / "Opensky_synth.bin"
+    rec.write_bytes(raw)
+    out = subprocess.run([exe, str(rec), "0"], capture_output=True, text=True, timeout=120,
+                         env=dict(os.environ, LD_LIBRARY_PATH=pkg))
+    assert out.returncode == 0, out.stderr
+    got = {int(m.group(1)): (float(m.group(2)), int(m.group(3)), int(m.group(4)))
+           for m in re.finditer(r"SV\[\s*(\d+)\] SNR = ([\d.]+), Code phase =\s*(\d+), Raw Doppler =\s*(-?\d+)", out.stdout)}
+    fine = {int(m.group(1)): float(m.group(2)) for m in re.finditer(r"SV\[\s*(\d+)\] Fine Doppler =\s*(-?[\d.]+)", out.stdout)}
+    file, signal, acq = gnssacq.initParameters(shape="opensky")
+    with api.Searcher(cfg_from(file, signal, acq, list(range(1, 33)))) as s:
+        rows = [r for r in s.search(raw[: s.if_bytes]) if r.acquired]
+        ff = s.fine_frequency(raw, int(acq.L), [r.prn for r in rows], [r.code_phase for r in rows])
+    assert sorted(got) == [r.prn for r in rows] and len(rows) >= 6
+    for r, f in zip(rows, ff):
+        snr, cp, dop = got[r.prn]
+        assert cp == r.code_phase and dop == int(r.doppler_hz) and abs(snr - r.snr_db) < 0.006
+        assert abs(fine[r.prn] - (f - signal.IF)) < 1e-3
