@@ -21,9 +21,93 @@ struct alignas(8) cf {
 };
 
 GNSS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
-GNSS_HD cf cadd(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
-GNSS_HD cf csub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
-GNSS_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// Complex arithmetic.  On the device every helper is ONE packed FP32 instruction of sm_100a
+// (FADD2 / FMUL2 / FFMA2 through __fadd2_rn / __fmul2_rn / __ffma2_rn): a complex value is a register
+// pair, the instruction's operand modifiers provide negation, the re<->im swap (.LO_HI) and the
+// broadcast of a scalar register or of a 32-bit immediate.  Same FMA-pipe time as two scalar
+// instructions, half the issue slots and half the code bytes (profiles/r02/fp32x2_probe.txt).
+// The host forms (CPU emulation of the index maps, tests/emu) compute the same values unfused.
+#if defined(__CUDA_ARCH__)
+#define GNSS_PACKED 1
+__device__ __forceinline__ float2 f2(cf a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ cf fc(float2 a) { return mk(a.x, a.y); }
+#endif
+
+GNSS_HD cf cadd(cf a, cf b) {
+#ifdef GNSS_PACKED
+    return fc(__fadd2_rn(f2(a), f2(b)));
+#else
+    return mk(a.x + b.x, a.y + b.y);
+#endif
+}
+GNSS_HD cf csub(cf a, cf b) {
+#ifdef GNSS_PACKED
+    return fc(__fadd2_rn(f2(a), make_float2(-b.x, -b.y)));
+#else
+    return mk(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * c, c real
+GNSS_HD cf cscale(cf a, float c) {
+#ifdef GNSS_PACKED
+    return fc(__fmul2_rn(f2(a), make_float2(c, c)));
+#else
+    return mk(a.x * c, a.y * c);
+#endif
+}
+// acc + a * c, c real
+GNSS_HD cf cfma(cf a, float c, cf acc) {
+#ifdef GNSS_PACKED
+    return fc(__ffma2_rn(f2(a), make_float2(c, c), f2(acc)));
+#else
+    return mk(acc.x + a.x * c, acc.y + a.y * c);
+#endif
+}
+// a - i*b  and  a + i*b
+GNSS_HD cf caddmi(cf a, cf b) {
+#ifdef GNSS_PACKED
+    return fc(__ffma2_rn(make_float2(b.y, b.x), make_float2(1.f, -1.f), f2(a)));
+#else
+    return mk(a.x + b.y, a.y - b.x);
+#endif
+}
+GNSS_HD cf caddpi(cf a, cf b) {
+#ifdef GNSS_PACKED
+    return fc(__ffma2_rn(make_float2(b.y, b.x), make_float2(-1.f, 1.f), f2(a)));
+#else
+    return mk(a.x - b.y, a.y + b.x);
+#endif
+}
+GNSS_HD cf cmul(cf a, cf b) {
+#ifdef GNSS_PACKED
+    const float2 t = __fmul2_rn(make_float2(a.x, a.x), f2(b));
+    return fc(__ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), t));
+#else
+    return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+// Scalar form (2 FMUL + 2 FFMA = 4 FMA-pipe cycles; the packed form above is 3 instructions but 5 pipe
+// cycles): used where the FMA pipe, not the issue slot, is the limiter (pass 1 of the search).
+GNSS_HD cf cmul_scalar(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// v * (c - i s) with (c, s) known: c*v + s*(v.y, -v.x)
+GNSS_HD cf cmul_cs(cf v, float c, float s) {
+#ifdef GNSS_PACKED
+    const float2 t = __fmul2_rn(f2(v), make_float2(c, c));
+    return fc(__ffma2_rn(make_float2(v.y, v.x), make_float2(s, -s), t));
+#else
+    return mk(v.x * c + v.y * s, v.y * c - v.x * s);
+#endif
+}
+// acc + |a|^2.  |a|^2 is rounded on its own before the addition: a block's power plane published by the
+// block-granular tail (search_kernel_coop) and added later must give the bits of the in-place accumulation.
+GNSS_HD float cnorm_acc(cf a, float acc) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(acc, fmaf(a.y, a.y, a.x * a.x));
+#else
+    return acc + (a.x * a.x + a.y * a.y);
+#endif
+}
 GNSS_HD float cnorm(cf a) { return a.x * a.x + a.y * a.y; }
 // read-only global load of one complex value (LDG.E.64.CONSTANT on the device)
 GNSS_HD cf ld_ro(const cf* p) {
@@ -113,23 +197,21 @@ struct Tw {
 template <int NUM, int DEN>
 GNSS_HD cf mul_tw(cf v) {
     constexpr int T = ((NUM % DEN) + DEN) % DEN;
+    constexpr float h = 0.70710678118654752440f;
     if constexpr (T == 0) {
         return v;
     } else if constexpr (4 * T == DEN) {          // -i
-        return mk(v.y, -v.x);
+        return caddmi(mk(0.f, 0.f), v);
     } else if constexpr (2 * T == DEN) {          // -1
         return mk(-v.x, -v.y);
     } else if constexpr (4 * T == 3 * DEN) {      // +i
-        return mk(-v.y, v.x);
-    } else if constexpr (8 * T == DEN) {          // (1-i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return mk((v.x + v.y) * h, (v.y - v.x) * h);
-    } else if constexpr (8 * T == 3 * DEN) {      // (-1-i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return mk((v.y - v.x) * h, -(v.x + v.y) * h);
+        return caddpi(mk(0.f, 0.f), v);
+    } else if constexpr (8 * T == DEN) {          // (1-i)/sqrt2 : h * (v - i v)
+        return cscale(caddmi(v, v), h);
+    } else if constexpr (8 * T == 3 * DEN) {      // (-1-i)/sqrt2 : -h * (v + i v)
+        return cscale(caddpi(v, v), -h);
     } else {
-        constexpr float c = Tw<T, DEN>::c, s = Tw<T, DEN>::s;
-        return mk(v.x * c + v.y * s, v.y * c - v.x * s);
+        return cmul_cs(v, Tw<T, DEN>::c, Tw<T, DEN>::s);
     }
 }
 

@@ -150,63 +150,101 @@ GNSS_HD void pass1_task(int task, int rank, const Loader& ld, cf* __restrict__ D
 }
 
 // ------------------------------------------------------------------ pass 2
-// tw125[j] = exp(-2*pi*i*j/125), j in [0,125).  Lane slot -> (a_local, b2, c'): the 16 lanes of a half-warp
-// walk 16 consecutive c' of ONE (a_local, b2) column.  Row stride 125 cf = 13 bank-pairs (mod 16), a
-// generator of Z16, so each half-warp touches 16 distinct bank-pairs: conflict-free 64-bit accesses, and
-// the twiddle reads are broadcasts.  Slots with c' >= Q idle (Q = 13: 3 of 16, Q = 29: 3 of 32); the
-// denser mapping that wraps into the next b2 cost 1.4-2.0x the shared-memory wavefronts (ncu r01).
+// Twiddle table: tw[b2*4 + (k1-1)] describes W125^(b2*k1) = c + i*s (s <= 0) as {c, 0, -s, s}: one 16-byte
+// (broadcast) load gives the scalar c and the register pair (-s, s) that the two packed instructions of the
+// complex multiply take as they are (u*w = c*u + (-s, s) (.) (u.y, u.x)).
+struct alignas(16) Tw4 {
+    float c, pad, ns, s;
+};
+GNSS_HD cf cmul_tw4(cf u, const Tw4& w) {
+#ifdef GNSS_PACKED
+    const float2 t = __fmul2_rn(f2(u), make_float2(w.c, w.c));
+    return fc(__ffma2_rn(make_float2(u.y, u.x), make_float2(w.ns, w.s), t));
+#else
+    return mk(u.x * w.c + u.y * w.ns, u.y * w.c + u.x * w.s);
+#endif
+}
+// Lane slot -> (a_local, b2, c'): the 16 lanes of a half-warp walk 16 consecutive c' of ONE (a_local, b2)
+// column.  Row stride 125 cf = 13 bank-pairs (mod 16), a generator of Z16, so each half-warp touches 16
+// distinct bank-pairs: conflict-free 64-bit accesses, and the twiddle reads are broadcasts.  Slots with
+// c' >= Q idle (Q = 13: 3 of 16, Q = 29: 3 of 32); the denser mapping that wraps into the next b2 cost
+// 1.4-2.0x the shared-memory wavefronts (ncu r01).
+// One cell = column ab = a_local*25 + b2, row c: DFT-5 over b1 (b = 25*b1 + b2) + the W125 twiddle.
 template <int Q, int R>
-GNSS_HD cf* pass2_ptr(int slot, cf* __restrict__ D, int& b2) {
+GNSS_HD cf* pass2_cell_ptr(int ab, int c, cf* __restrict__ D, int& b2) {
     using S = Split<Q, R>;
-    const int hw = slot >> 4, l = slot & 15;
-    const int h = hw % S::P2_H, ab = hw / S::P2_H;
-    b2 = ab % 25;
-    const int al = ab / 25;
-    const int c = h * 16 + l;
-    if (c >= Q) return nullptr;
-    return D + al * S::RS + c * 125 + b2;
+    if constexpr (S::A == 1) {
+        b2 = ab;
+        return D + c * 125 + ab;
+    } else {
+        const int al = ab / 25;
+        b2 = ab - al * 25;
+        return D + al * S::RS + c * 125 + b2;
+    }
 }
 template <int Q, int R>
-GNSS_HD void pass2_task(int slot, cf* __restrict__ D, const cf* __restrict__ tw125) {
+GNSS_HD void pass2_cell(int ab, int c, cf* __restrict__ D, const Tw4* __restrict__ tw) {
     int b2;
-    cf* p = pass2_ptr<Q, R>(slot, D, b2);
-    if (!p) return;
+    cf* p = pass2_cell_ptr<Q, R>(ab, c, D, b2);
     cf u[5] = {p[0], p[25], p[50], p[75], p[100]};
+    const Tw4* w = tw + 4 * b2;
+    const Tw4 w1 = w[0], w2 = w[1], w3 = w[2], w4 = w[3];
     dft_odd<5>(u);
     p[0] = u[0];
-    static_for<1, 5>([&](auto kc) {
-        constexpr int K1 = decltype(kc)::value;
-        p[25 * K1] = cmul(u[K1], tw125[b2 * K1]);
-    });
+    p[25] = cmul_tw4(u[1], w1);
+    p[50] = cmul_tw4(u[2], w2);
+    p[75] = cmul_tw4(u[3], w3);
+    p[100] = cmul_tw4(u[4], w4);
 }
-// two slots at once: all loads, then all math, then all stores (memory-level parallelism)
+// two cells of one row at once: all loads, then all math, then all stores (memory-level parallelism)
 template <int Q, int R>
-GNSS_HD void pass2_task2(int t0, int t1, cf* __restrict__ D, const cf* __restrict__ tw125) {
+GNSS_HD void pass2_cell2(int ab0, int ab1, int c, cf* __restrict__ D, const Tw4* __restrict__ tw) {
     int b20, b21;
-    cf* p0 = pass2_ptr<Q, R>(t0, D, b20);
-    cf* p1 = pass2_ptr<Q, R>(t1, D, b21);
-    if (!p0 || !p1) {                    // same c' for both (t1 - t0 is a multiple of 16): both idle or neither
-        if (p0) pass2_task<Q, R>(t0, D, tw125);
-        if (p1) pass2_task<Q, R>(t1, D, tw125);
-        return;
-    }
+    cf* p0 = pass2_cell_ptr<Q, R>(ab0, c, D, b20);
+    cf* p1 = pass2_cell_ptr<Q, R>(ab1, c, D, b21);
     cf u[5] = {p0[0], p0[25], p0[50], p0[75], p0[100]};
     cf v[5] = {p1[0], p1[25], p1[50], p1[75], p1[100]};
-    cf wu[5], wv[5];
-    static_for<1, 5>([&](auto kc) {
-        constexpr int K1 = decltype(kc)::value;
-        wu[K1] = tw125[b20 * K1];
-        wv[K1] = tw125[b21 * K1];
-    });
+    const Tw4* wu = tw + 4 * b20;
+    const Tw4* wv = tw + 4 * b21;
+    const Tw4 wu1 = wu[0], wu2 = wu[1], wu3 = wu[2], wu4 = wu[3];
+    const Tw4 wv1 = wv[0], wv2 = wv[1], wv3 = wv[2], wv4 = wv[3];
     dft_odd<5>(u);
     dft_odd<5>(v);
     p0[0] = u[0];
     p1[0] = v[0];
-    static_for<1, 5>([&](auto kc) {
-        constexpr int K1 = decltype(kc)::value;
-        p0[25 * K1] = cmul(u[K1], wu[K1]);
-        p1[25 * K1] = cmul(v[K1], wv[K1]);
-    });
+    p0[25] = cmul_tw4(u[1], wu1);
+    p1[25] = cmul_tw4(v[1], wv1);
+    p0[50] = cmul_tw4(u[2], wu2);
+    p1[50] = cmul_tw4(v[2], wv2);
+    p0[75] = cmul_tw4(u[3], wu3);
+    p1[75] = cmul_tw4(v[3], wv3);
+    p0[100] = cmul_tw4(u[4], wu4);
+    p1[100] = cmul_tw4(v[4], wv4);
+}
+// The whole pass for a CTA of T threads.  Half-warp hw = tid/16 (+ T/16 per round) serves row block
+// h = hw % P2_H of column ab = hw / P2_H; T/16 is a multiple of P2_H, so a thread's row c is fixed and its
+// columns are ab0, ab0 + G, ab0 + 2G, ... : no per-round index arithmetic beyond one addition.
+template <int Q, int R, int T>
+GNSS_HD void pass2_cta(int tid, cf* __restrict__ D, const Tw4* __restrict__ tw) {
+    using S = Split<Q, R>;
+    static_assert((T / 16) % S::P2_H == 0, "half-warps per CTA must be a multiple of the row blocks");
+    constexpr int G = (T / 16) / S::P2_H;          // columns per round
+    constexpr int NAB = S::A * 25;
+    const int hw = tid >> 4;
+    const int c = (hw % S::P2_H) * 16 + (tid & 15);
+    if (c >= Q) return;
+    int ab = hw / S::P2_H;
+    for (; ab + G < NAB; ab += 2 * G) pass2_cell2<Q, R>(ab, ab + G, c, D, tw);
+    if (ab < NAB) pass2_cell<Q, R>(ab, c, D, tw);
+}
+// slot form (CPU emulation): slot = half-warp * 16 + lane over all P2_TASKS lane slots
+template <int Q, int R>
+GNSS_HD void pass2_task(int slot, cf* __restrict__ D, const Tw4* __restrict__ tw) {
+    using S = Split<Q, R>;
+    const int hw = slot >> 4, l = slot & 15;
+    const int c = (hw % S::P2_H) * 16 + l;
+    if (c >= Q) return;
+    pass2_cell<Q, R>(hw / S::P2_H, c, D, tw);
 }
 
 // ------------------------------------------------------------------ pass 3
@@ -328,7 +366,7 @@ struct SearchLoader {
         return c;
     }
     template <int Q, int C>
-    GNSS_HD cf at(const Ctx& c) const { return cmul(ld_ro(c.pc + C * 125), ld_ro(c.px + C * 125)); }
+    GNSS_HD cf at(const Ctx& c) const { return cmul_scalar(ld_ro(c.pc + C * 125), ld_ro(c.px + C * 125)); }
     template <int Q>
     GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
         const int as = (a - sa) & 15;
@@ -338,7 +376,7 @@ struct SearchLoader {
         const cf* px = x + (as * (2 * Q - 1) + c0) * 125 + bs;
         static_for<0, Q>([&](auto c_) {
             constexpr int C = decltype(c_)::value;
-            z[C] = cmul(ld_ro(pc + C * 125), ld_ro(px + C * 125));
+            z[C] = cmul_scalar(ld_ro(pc + C * 125), ld_ro(px + C * 125));
         });
     }
 };
@@ -353,8 +391,8 @@ struct PowerAccumStorer {
             constexpr int AP = (I / 4) + 4 * (I % 4);
             cf* p = reinterpret_cast<cf*>(acc + AP * CHX + t);
             cf v = *p;
-            v.x += cnorm(w0[I]);
-            v.y += cnorm(w1[I]);
+            v.x = cnorm_acc(w0[I], v.x);
+            v.y = cnorm_acc(w1[I], v.y);
             *p = v;
         });
     }
@@ -366,8 +404,8 @@ struct PowerAccumStorer {
             constexpr int AP = (I / 4) + 4 * (I % 4);            // a' = k1 + 4*k2
             cf* p = reinterpret_cast<cf*>(acc + AP * CH + t);    // t even, CH even: 8-byte aligned
             cf v = *p;
-            v.x += cnorm(w0[I]);
-            v.y += cnorm(w1[I]);
+            v.x = cnorm_acc(w0[I], v.x);
+            v.y = cnorm_acc(w1[I], v.y);
             *p = v;
         });
     }

@@ -31,6 +31,9 @@ struct SearchArgs {
     float* partial;        // coop variant: [groups][K-1][R][ACC_ELEMS] power planes of tail-row blocks handed to the finishing group
     unsigned* part_ctr;    // coop variant: [groups][R] published planes (zeroed before the launch)
     int row_granular;      // coop variant: deal out whole rows only (no hand-over; sums independent of the group count)
+#ifdef GNSS_TIMELINE       // experiment builds only (profiles/timeline.py): clock64 stamps of one iteration of group 0
+    unsigned long long* timeline;   // [R][warps][32]
+#endif
 };
 
 struct WipeArgs {

@@ -62,18 +62,15 @@ __device__ __forceinline__ void cl_sync() {
 }
 
 template <int Q, int R, int T>
-__device__ __forceinline__ void pass2_all(cf* D, const cf* tw, int tid) {
-    using S = Split<Q, R>;
-    int t = tid;
-    for (; t + T < S::P2_TASKS; t += 2 * T) pass2_task2<Q, R>(t, t + T, D, tw);
-    if (t < S::P2_TASKS) pass2_task<Q, R>(t, D, tw);
+__device__ __forceinline__ void pass2_all(cf* D, const Tw4* tw, int tid) {
+    pass2_cta<Q, R, T>(tid, D, tw);
 }
 
 // pass 3 over the CTA.  (A 5-lanes-per-task cooperative form for the few leftover tasks -- P3_TASKS is
 // just above the thread count -- was measured in r01 and LOST 8 %: its address arithmetic raised the
 // register pressure of the surrounding code, which sits at the 128-register limit.  Plain rounds it is.)
 template <int Q, int R, int T>
-__device__ __forceinline__ void pass3_all(cf* D, const cf* tw, int tid) {
+__device__ __forceinline__ void pass3_all(cf* D, const Tw4* tw, int tid) {
     using S = Split<Q, R>;
     (void)tw;
     for (int t = tid; t < S::P3_TASKS; t += T) pass3_task<Q, R>(t, D);
@@ -95,17 +92,19 @@ struct Smem {
     static constexpr size_t d_bytes = (size_t)S::D_ELEMS * sizeof(cf);
     static constexpr size_t acc_floats = S::ACC_ELEMS > SplitX<Q, R>::ACC_ELEMS ? S::ACC_ELEMS : SplitX<Q, R>::ACC_ELEMS;
     static constexpr size_t acc_bytes = acc_floats * sizeof(float);
-    static constexpr size_t tw_bytes = 125 * sizeof(cf);
+    static constexpr size_t tw_bytes = 100 * sizeof(Tw4);
     static constexpr size_t red_bytes = ((sizeof(RedScratch) + 15) / 16) * 16;
     static constexpr size_t transform = d_bytes + tw_bytes;
     static constexpr size_t search = d_bytes + acc_bytes + tw_bytes + red_bytes;
 };
 
-__device__ __forceinline__ void fill_tw125(cf* tw, int tid, int T) {
-    for (int j = tid; j < 125; j += T) {
+__device__ __forceinline__ void fill_tw125(Tw4* tw, int tid, int T) {
+    for (int j = tid; j < 100; j += T) {          // entry j = b2*4 + (k1-1): W125^(b2*k1)
         double s, c;
-        sincospi(-2.0 * (double)j / 125.0, &s, &c);
-        tw[j] = mk((float)c, (float)s);
+        sincospi(-2.0 * (double)((j >> 2) * ((j & 3) + 1)) / 125.0, &s, &c);
+        Tw4 w;
+        w.c = (float)c; w.pad = 0.f; w.ns = -(float)s; w.s = (float)s;
+        tw[j] = w;
     }
 }
 
@@ -144,7 +143,7 @@ __device__ __forceinline__ void block_reduce(float& v, int& m, double& s, RedScr
 // passes 1-4 of one transform; cluster-wide barriers around the DSMEM pass
 template <int Q, int R, int T, class Loader, class Storer>
 __device__ __forceinline__ void unit_device(const Loader& ld, Storer& st, cf* D, cf* const* Dall,
-                                            const cf* tw, int rank, int tid) {
+                                            const Tw4* tw, int rank, int tid) {
     using S = Split<Q, R>;
     for (int t = tid; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
     __syncthreads();
@@ -162,7 +161,7 @@ __device__ __forceinline__ void unit_device(const Loader& ld, Storer& st, cf* D,
 // Precondition: one cl_arrive() is pending on entry; postcondition: one is pending on exit.
 template <int Q, int R, int T, class Loader, class Storer>
 __device__ __forceinline__ void unit_device_pipelined(const Loader& ld, Storer& st, cf* D, cf* const* Dall,
-                                                      const cf* tw, int rank, int tid) {
+                                                      const Tw4* tw, int rank, int tid) {
     using S = Split<Q, R>;
     {
         cf z[Q];
@@ -198,7 +197,7 @@ __device__ __forceinline__ void unit_device_pipelined(const Loader& ld, Storer& 
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) code_kernel(CodeArgs a) {
     GNSS_KERNEL_PROLOGUE
-    cf* tw = D + S::D_ELEMS;
+    Tw4* tw = reinterpret_cast<Tw4*>(D + S::D_ELEMS);
     fill_tw125(tw, tid, T);
     __syncthreads();
     CodeLoader ld{a.scode + (size_t)unit * G::N};
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(T, MINB) code_kernel(CodeArgs a) {
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) wipe_kernel(WipeArgs a) {
     GNSS_KERNEL_PROLOGUE
-    cf* tw = D + S::D_ELEMS;
+    Tw4* tw = reinterpret_cast<Tw4*>(D + S::D_ELEMS);
     fill_tw125(tw, tid, T);
     __syncthreads();
     const int base = unit / a.K, k = unit - base * a.K;
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(T, MINB) wipe_kernel(WipeArgs a) {
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
     GNSS_KERNEL_PROLOGUE
-    cf* tw = D + S::D_ELEMS;
+    Tw4* tw = reinterpret_cast<Tw4*>(D + S::D_ELEMS);
     fill_tw125(tw, tid, T);
     __syncthreads();
     NaturalLoader ld{a.in + (size_t)unit * G::N};
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) fine_kernel(FineArgs a) {
     GNSS_KERNEL_PROLOGUE
-    cf* tw = D + S::D_ELEMS;
+    Tw4* tw = reinterpret_cast<Tw4*>(D + S::D_ELEMS);
     fill_tw125(tw, tid, T);
     __syncthreads();
     const int n2 = unit % a.L, r = (unit / a.L) % a.K, sv = unit / (a.L * a.K);
@@ -266,8 +265,8 @@ template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
     GNSS_KERNEL_PROLOGUE
     float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
-    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
-    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    Tw4* tw = reinterpret_cast<Tw4*>(acc + Smem<Q, R>::acc_floats);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 100);
     const int row = unit;                       // row = bin * P + prn_index (PRN fastest: rows in
     const int p = row % a.P, b = row / a.P;     // flight share the same forward spectra in L2)
 
@@ -364,8 +363,8 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
     GNSS_KERNEL_PROLOGUE
     (void)Dall;
     float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);
-    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
-    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    Tw4* tw = reinterpret_cast<Tw4*>(acc + Smem<Q, R>::acc_floats);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 100);
     const int ncl = gridDim.x / R, slot = unit;
     cf* xch = a.scratch + (size_t)slot * 2 * 16 * S::RS;
     fill_tw125(tw, tid, T);
@@ -495,7 +494,11 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
 // before it).  Gains over the cluster kernels: every SM is usable (4-CTA clusters leave 16 of 148 SMs
 // idle, ncu r01: 33 clusters resident), and only one thread pays the release fence.
 __device__ __forceinline__ void group_arrive(unsigned* ctr) {
+#ifdef GNSS_EXPERIMENT_NOFENCE   // timing only: results invalid
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#else
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#endif
 }
 __device__ __forceinline__ void group_arrive_n(unsigned* ctr, unsigned n) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(n) : "memory");
@@ -563,6 +566,11 @@ __device__ __noinline__ void merge_planes(float* acc, const float* planes, int n
 #else
 #define GNSS_KSYNC() __syncthreads()
 #endif
+#ifdef GNSS_TIMELINE
+#define GNSS_TL(i) do { if (tl_iter == 6 && group == 0 && (tid & 31) == 0) a.timeline[(rank * (T / 32) + (tid >> 5)) * 32 + (i)] = clock64(); } while (0)
+#else
+#define GNSS_TL(i) do { } while (0)
+#endif
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     using S = Split<Q, R>;
@@ -580,8 +588,8 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* D = reinterpret_cast<cf*>(smem_raw);
     float* acc = reinterpret_cast<float*>(D + S::D_ELEMS);                 // [16][CHX] (XT layout)
-    cf* tw = reinterpret_cast<cf*>(acc + Smem<Q, R>::acc_floats);
-    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 125);
+    Tw4* tw = reinterpret_cast<Tw4*>(acc + Smem<Q, R>::acc_floats);
+    RedScratch* rs = reinterpret_cast<RedScratch*>(tw + 100);
     constexpr size_t XBUF = (size_t)16 * GX::RSX;                          // cf per exchange buffer
     cf* xch = a.scratch + (size_t)group * 2 * XBUF;
     unsigned* ctr = a.group_ctr + group;
@@ -639,7 +647,14 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     // pass 3 leaves its results directly in the L2-resident exchange buffer (transposed "XT" layout: the 25
     // stores of a task are coalesced across the warp) -- no shared-memory write, no copy-out pass
     for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, xch + (size_t)rank * S::A * GX::RSX);
+#ifdef GNSS_TIMELINE
+    int tl_iter = 0;
+#endif
     for (;;) {
+#ifdef GNSS_TIMELINE
+        ++tl_iter;
+#endif
+        GNSS_TL(0);
         const bool last_of_part = (left == 1);
         const bool more = !last_of_part || i + 1 < count_parts();
         const cf* buf = xch + (size_t)par * XBUF;          // rows of the current block (all CTAs write into it)
@@ -657,13 +672,19 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             cf z[Q];
             const bool has = tid < S::P1_TASKS;
             if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+            GNSS_TL(1);
             GNSS_KSYNC();                          // every thread is done with pass 3 of the current block
+            GNSS_TL(2);
             if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier): its rows are in L2
+            GNSS_TL(3);
             if (has) pass1_store<Q, R>(tid, z, D);
             if constexpr (S::P1_TASKS > T)
                 for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+            GNSS_TL(4);
             GNSS_KSYNC();
+            GNSS_TL(5);
             pass2_all<Q, R, T>(D, tw, tid2);
+            GNSS_TL(6);
         } else {
             GNSS_KSYNC();
             if (tid == 0) group_arrive(ctr);
@@ -671,13 +692,17 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
 #ifndef GNSS_EXPERIMENT_NOSPIN
         if (tid == 0) group_spin(ctr, target);     // acquire: everybody's rows of this block are in L2
 #endif
+        GNSS_TL(7);
         GNSS_KSYNC();
+        GNSS_TL(8);
         // pass 4 of this block and pass 3 of the next share a barrier interval: the L2 latency of the
         // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
         // barrier to add slack was measured in r01 and lost 3 %.)
         for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
+        GNSS_TL(9);
         if (more)
             for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
+        GNSS_TL(10);
         if (later) {
             // A later part of a tail row that an earlier group finishes: publish this block's power plane on
             // its own (slot = block index in the row, in the finisher's slab), so that the finisher can add the

@@ -1,7 +1,7 @@
 // gnss_radix.h -- register-resident forward DFT butterflies (exp(-2*pi*i*nk/R)).
 //
-//   dft_odd<Q>   any odd length (5, 13, 29, ...): symmetric-pair form, all
-//                coefficients compile-time immediates, 2H + H(4H+4) FP ops, H=(Q-1)/2
+//   dft_odd<Q>   any odd length (5, 13, 29, ...): symmetric-pair form, all coefficients compile-time
+//                immediates of packed FFMA2 instructions: 3H + 2H*H + 2H packed ops, H=(Q-1)/2
 //   dft4, dft16  16 = 4 x 4 Cooley-Tukey
 //   dft25        25 = 5 x 5 Cooley-Tukey
 //
@@ -29,35 +29,30 @@ GNSS_HD void dft_odd(cf (&v)[Q]) {
     v[0] = s0;
     static_for<1, H + 1>([&](auto kc) {
         constexpr int K = decltype(kc)::value;
-        float cx = x0.x, cy = x0.y, sx = 0.f, sy = 0.f;
+        // C = x0 + sum_J cos(2 pi JK/Q) a[J],  S = sum_J sin(2 pi JK/Q) b[J]  (one packed FMA per term)
+        cf C = x0, S = mk(0.f, 0.f);
         static_for<1, H + 1>([&](auto jc) {
             constexpr int J = decltype(jc)::value;
             constexpr int T = (J * K) % Q;
-            constexpr float c = Tw<T, Q>::c, s = Tw<T, Q>::s;
-            cx += c * a[J].x;
-            cy += c * a[J].y;
-            sx += s * b[J].x;
-            sy += s * b[J].y;
+            C = cfma(a[J], Tw<T, Q>::c, C);
+            if constexpr (J == 1) S = cscale(b[J], Tw<T, Q>::s);
+            else S = cfma(b[J], Tw<T, Q>::s, S);
         });
         // X[K] = C - i S ; X[Q-K] = C + i S
-        v[K] = mk(cx + sy, cy - sx);
-        v[Q - K] = mk(cx - sy, cy + sx);
+        v[K] = caddmi(C, S);
+        v[Q - K] = caddpi(C, S);
     });
 }
 
 // Same transform, input-major ("streaming") form: inputs are fetched pair by pair through `get`
 // (get(integral_constant<int,C>) -> cf) and folded into all (Q-1)/2 output accumulators at once, so the
-// arithmetic on the first pairs overlaps the memory latency of the later ones.  4*H accumulators live.
+// arithmetic on the first pairs overlaps the memory latency of the later ones.  2*H complex accumulators live.
 template <int Q, class Get>
 GNSS_HD void dft_odd_stream(Get&& get, cf (&v)[Q]) {
     static_assert(Q % 2 == 1 && Q >= 3, "odd length");
     constexpr int H = (Q - 1) / 2;
     const cf x0 = get(std::integral_constant<int, 0>{});
-    float cx[H + 1], cy[H + 1], sx[H + 1], sy[H + 1];
-    static_for<1, H + 1>([&](auto kc) {
-        constexpr int K = decltype(kc)::value;
-        cx[K] = x0.x; cy[K] = x0.y; sx[K] = 0.f; sy[K] = 0.f;
-    });
+    cf C[H + 1], S[H + 1];
     cf s0 = x0;
     static_for<1, H + 1>([&](auto jc) {
         constexpr int J = decltype(jc)::value;
@@ -68,18 +63,20 @@ GNSS_HD void dft_odd_stream(Get&& get, cf (&v)[Q]) {
         static_for<1, H + 1>([&](auto kc) {
             constexpr int K = decltype(kc)::value;
             constexpr int T = (J * K) % Q;
-            constexpr float c = Tw<T, Q>::c, s = Tw<T, Q>::s;
-            cx[K] += c * a.x;
-            cy[K] += c * a.y;
-            sx[K] += s * b.x;
-            sy[K] += s * b.y;
+            if constexpr (J == 1) {
+                C[K] = cfma(a, Tw<T, Q>::c, x0);
+                S[K] = cscale(b, Tw<T, Q>::s);
+            } else {
+                C[K] = cfma(a, Tw<T, Q>::c, C[K]);
+                S[K] = cfma(b, Tw<T, Q>::s, S[K]);
+            }
         });
     });
     v[0] = s0;
     static_for<1, H + 1>([&](auto kc) {
         constexpr int K = decltype(kc)::value;
-        v[K] = mk(cx[K] + sy[K], cy[K] - sx[K]);
-        v[Q - K] = mk(cx[K] - sy[K], cy[K] + sx[K]);
+        v[K] = caddmi(C[K], S[K]);
+        v[Q - K] = caddpi(C[K], S[K]);
     });
 }
 
@@ -87,8 +84,16 @@ GNSS_HD void dft4(cf& x0, cf& x1, cf& x2, cf& x3) {
     const cf t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
     x0 = cadd(t0, t2);
     x2 = csub(t0, t2);
-    x1 = mk(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
-    x3 = mk(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+    x1 = caddmi(t1, t3);   // t1 - i t3
+    x3 = caddpi(t1, t3);   // t1 + i t3
+}
+// dft4 whose input x2 still has to be multiplied by -i (the W16^4 twiddle): folded into the first butterfly
+GNSS_HD void dft4_x2mi(cf& x0, cf& x1, cf& x2, cf& x3) {
+    const cf t0 = caddmi(x0, x2), t1 = caddpi(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    x1 = caddmi(t1, t3);
+    x3 = caddpi(t1, t3);
 }
 
 // in: v[4*n1 + n2] = x[4*n1 + n2]; out: v[4*k1 + k2] = X[k1 + 4*k2]
@@ -98,12 +103,14 @@ GNSS_HD void dft16(cf (&v)[16]) {
         dft4(v[N2], v[4 + N2], v[8 + N2], v[12 + N2]);     // over n1 -> k1 at v[4*k1 + N2]
         static_for<1, 4>([&](auto k1c) {
             constexpr int K1 = decltype(k1c)::value;
-            v[4 * K1 + N2] = mul_tw<N2 * K1, 16>(v[4 * K1 + N2]);
+            if constexpr (N2 * K1 != 4) v[4 * K1 + N2] = mul_tw<N2 * K1, 16>(v[4 * K1 + N2]);
         });
     });
     static_for<0, 4>([&](auto k1c) {
         constexpr int K1 = decltype(k1c)::value;
-        dft4(v[4 * K1], v[4 * K1 + 1], v[4 * K1 + 2], v[4 * K1 + 3]);   // over n2 -> k2
+        // over n2 -> k2; v[4*2 + 2] carries the pending -i (N2*K1 == 4)
+        if constexpr (K1 == 2) dft4_x2mi(v[8], v[9], v[10], v[11]);
+        else dft4(v[4 * K1], v[4 * K1 + 1], v[4 * K1 + 2], v[4 * K1 + 3]);
     });
 }
 

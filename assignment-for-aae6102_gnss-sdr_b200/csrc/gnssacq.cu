@@ -851,6 +851,12 @@ int gnssacq_set_stream(gnssacq_handle* h, void* s) {
     return GNSSACQ_OK;
 }
 
+#ifdef GNSS_TIMELINE
+static unsigned long long* g_timeline = nullptr;
+extern "C" int gnssacq_debug_timeline(unsigned long long* out /*[16*16*32]*/) {
+    return cudaMemcpy(out, g_timeline, 16 * 16 * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -4;
+}
+#endif
 static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = nullptr) {
     cudaStream_t s = h->stream;
     h->launches = 0;
@@ -894,6 +900,13 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.partial = h->d_partial;
     sa.part_ctr = h->d_group_ctr ? h->d_group_ctr + h->coop_groups : nullptr;
     sa.row_granular = h->d_partial ? 0 : 1;
+#ifdef GNSS_TIMELINE
+    static unsigned long long* d_timeline = nullptr;
+    if (!d_timeline) { CU(cudaMalloc(&d_timeline, 16 * 16 * 32 * sizeof(unsigned long long))); }
+    CU(cudaMemsetAsync(d_timeline, 0, 16 * 16 * 32 * sizeof(unsigned long long), s));
+    sa.timeline = d_timeline;
+    g_timeline = d_timeline;
+#endif
     if (h->coop_groups > 0) {
         CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * (1 + h->ops->R) * sizeof(unsigned), s));
         CU(h->ops->launch_search_coop(sa, h->coop_groups, s));

@@ -1,0 +1,5 @@
+// One engine variant per translation unit (they compile in parallel): Q = 29, 4 CTAs x 512 threads per transform.
+#include "../gnss_kernels.cuh"
+namespace gnss {
+extern const VariantOps gnss_variant_29_4_512 = Variant<29, 4, 512, 1>::ops();
+}  // namespace gnss

@@ -16,7 +16,7 @@ import numpy as np
 
 GNSSACQ_MAX_PRN = 64
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("GNSSACQ_LIB") or os.path.join(_HERE, "libgnssacq.so")   # GNSSACQ_LIB: experiment builds
+LIB_PATH = os.path.join(_HERE, "libgnssacq.so")
 
 
 class GnssAcqError(RuntimeError):

@@ -7,7 +7,9 @@ import sys
 CHILD = r'''
 import os
 import sys
-sys.path[:0] = ["/root/repo", "/root/repo/assignment-for-aae6102_gnss-sdr_b200"]
+sys.path.insert(0, "/root/repo/profiles")
+import explib
+explib.use_lib(os.environ.get("AB_LIB"))
 import gnssacq
 from gnssacq import api
 from gnssacq.synth import urban_recording, opensky_recording
@@ -35,7 +37,7 @@ for i, a in enumerate(sys.argv):
 best = {}
 for r in range(rounds):
     for name, path in libs:
-        env = dict(os.environ, GNSSACQ_LIB=os.path.abspath(path.split("@")[0]))
+        env = dict(os.environ, AB_LIB=os.path.abspath(path.split("@")[0]))
         if "@" in path:                                  # name=lib.so@1 -> work_split=1
             env["AB_WORK_SPLIT"] = path.split("@")[1]
         out = subprocess.run([sys.executable, "-c", CHILD, prns], env=env, capture_output=True, text=True)

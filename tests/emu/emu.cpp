@@ -13,28 +13,25 @@ using namespace gnss;
 
 template <int Q, int R, class Loader, class Storer>
 static void run_unit(const Loader& ld, Storer* st /*R storers*/, std::vector<std::vector<cf>>& D,
-                     const std::vector<cf>& tw) {
+                     const std::vector<Tw4>& tw) {
     using S = Split<Q, R>;
     cf* Dall[R];
     for (int r = 0; r < R; ++r) Dall[r] = D[r].data();
     for (int r = 0; r < R; ++r)
         for (int t = 0; t < S::P1_TASKS; ++t) pass1_task<Q, R>(t, r, ld, Dall[r]);
-    for (int r = 0; r < R; ++r) {
-        int t = 0;                                   // exercise the two-task form as the kernels do
-        for (; t + 1 < S::P2_TASKS; t += 2) pass2_task2<Q, R>(t, t + 1, Dall[r], tw.data());
-        if (t < S::P2_TASKS) pass2_task<Q, R>(t, Dall[r], tw.data());
-    }
+    for (int r = 0; r < R; ++r)                      // the CTA-wide form the kernels call, thread by thread
+        for (int tid = 0; tid < 128; ++tid) pass2_cta<Q, R, 128>(tid, Dall[r], tw.data());
     for (int r = 0; r < R; ++r)
         for (int t = 0; t < S::P3_TASKS; ++t) pass3_task<Q, R>(t, Dall[r]);
     for (int r = 0; r < R; ++r)
         for (int t = 0; t < S::P4_TASKS; ++t) pass4_task<Q, R>(t, r, Dall, st[r]);
 }
 
-static std::vector<cf> make_tw125() {
-    std::vector<cf> tw(125);
-    for (int j = 0; j < 125; ++j) {
-        double a = -2.0 * 3.14159265358979323846 * j / 125.0;
-        tw[j] = mk((float)cos(a), (float)sin(a));
+static std::vector<Tw4> make_tw125() {
+    std::vector<Tw4> tw(100);                        // entry b2*4 + (k1-1): W125^(b2*k1), as fill_tw125 builds it
+    for (int j = 0; j < 100; ++j) {
+        double a = -2.0 * 3.14159265358979323846 * ((j >> 2) * ((j & 3) + 1)) / 125.0;
+        tw[j] = Tw4{(float)cos(a), 0.f, -(float)sin(a), (float)sin(a)};
     }
     return tw;
 }
