@@ -521,6 +521,7 @@ struct gnssacq_handle {
     int l2x_clusters = 0;          // > 0: use the L2-exchange persistent search kernel with this many clusters
     int coop_groups = 0;           // > 0: use the cluster-free cooperative kernel with this many CTA groups
     unsigned* d_group_ctr = nullptr;
+    const gnssacq_result* d_last_rows = nullptr;   // where the last enqueued search wrote its rows (d_res or the caller's buffer)
     Candidate* d_row_slots = nullptr;
     float* d_partial = nullptr;    // cooperative kernel: accumulators of row parts handed between groups
     long long* d_sums = nullptr;
@@ -921,6 +922,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
                                                     h->cfg.freq_step_hz, h->cfg.snr_threshold_db, h->d_prn,
                                                     d_out ? d_out : h->d_res);
     CU(cudaGetLastError());
+    h->d_last_rows = d_out ? d_out : h->d_res;
     h->launches += 1;
     CU(cudaEventRecord(h->ev[4], s));
     return GNSSACQ_OK;
@@ -945,12 +947,15 @@ int gnssacq_enqueue_device_out(gnssacq_handle* h, const void* d_if, size_t nbyte
 }
 
 int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* st) {
-    if (!h || !out) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (!h || (!out && !st)) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (!h->d_last_rows) return fail(h, GNSSACQ_ERR_STATE, "no search has been enqueued on this handle");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemcpyAsync(h->h_res, h->d_res, h->P * sizeof(gnssacq_result), cudaMemcpyDeviceToHost, h->stream));
+    // rows of the LAST enqueued search, wherever it wrote them (its own table, or the caller's device buffer of
+    // gnssacq_enqueue_device_out); out == NULL: timings only
+    if (out) CU(cudaMemcpyAsync(h->h_res, h->d_last_rows, h->P * sizeof(gnssacq_result), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev[5], h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    std::memcpy(out, h->h_res, h->P * sizeof(gnssacq_result));
+    if (out) std::memcpy(out, h->h_res, h->P * sizeof(gnssacq_result));
     if (st) {
         std::memset(st, 0, sizeof(*st));
         if (h->have_h2d) cudaEventElapsedTime(&st->h2d_ms, h->ev[0], h->ev[1]);
@@ -1016,12 +1021,11 @@ int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n, const void* if_sa
 // independent searches.  Window i+1 is staged (host memcpy into pinned memory) and copied to HBM on a copy
 // stream while window i is searched; two staging pairs, events in both directions, one D2H of all rows at the
 // end.  Rows of window i are out[i*n_prn .. (i+1)*n_prn) and equal what gnssacq_search returns for that window.
-int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
-                  gnssacq_result* out, gnssacq_stats* st) {
-    if (!h || !windows || !out || n_windows < 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
-    if (nbytes_each < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "window shorter than noncoh_blocks*coh_ms ms");
-    for (int i = 0; i < n_windows; ++i)
-        if (!windows[i]) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL window");
+// `fill(i, dst)` puts window i (if_bytes bytes) into pinned staging memory: a memcpy from the caller's window
+// (gnssacq_sweep) or an fseek + fread straight from the recording (gnssacq_sweep_file).
+extern "C++" {
+template <class Fill>
+static int sweep_impl(gnssacq_handle* h, int32_t n_windows, gnssacq_result* out, gnssacq_stats* st, Fill&& fill) {
     if (n_windows == 0) return GNSSACQ_OK;
     CU(cudaSetDevice(h->device));
     if (!h->copy_stream) {
@@ -1046,9 +1050,11 @@ int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windo
     for (int i = 0; i < n_windows; ++i) {
         const int b = i & 1;
         if (i >= 2) CU(cudaEventSynchronize(h->ev_copied[b]));              // pinned buffer b has left for HBM
-        std::memcpy(h_buf[b], windows[i], h->if_bytes);
+        { const int rc = fill(i, h_buf[b]); if (rc != GNSSACQ_OK) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream); return rc; } }
         if (i >= 2) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[b], 0));   // search i-2 is done with d_buf[b]
-        else CU(cudaStreamWaitEvent(h->copy_stream, h->ev[4], 0));          // (first use: after whatever ran last)
+        else if (i == 0) CU(cudaStreamWaitEvent(h->copy_stream, h->ev[4], 0));      // d_if: after whatever this handle ran last
+        // (i == 1: d_if2 / h_if2 are touched by sweeps only, and every sweep ends with a stream sync: no wait, so
+        //  the copy of window 1 overlaps the search of window 0)
         CU(cudaMemcpyAsync(d_buf[b], h_buf[b], h->if_bytes, cudaMemcpyHostToDevice, h->copy_stream));
         CU(cudaEventRecord(h->ev_copied[b], h->copy_stream));
         CU(cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
@@ -1077,6 +1083,41 @@ int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windo
         st->work_split = h->d_partial ? 2 : 1;
     }
     return GNSSACQ_OK;
+}
+
+}  // extern "C++"
+
+int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
+                  gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !windows || !out || n_windows < 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (nbytes_each < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "window shorter than noncoh_blocks*coh_ms ms");
+    for (int i = 0; i < n_windows; ++i)
+        if (!windows[i]) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL window");
+    return sweep_impl(h, n_windows, out, st, [&](int i, void* dst) {
+        std::memcpy(dst, windows[i], h->if_bytes);
+        return (int)GNSSACQ_OK;
+    });
+}
+
+// The same sweep straight from a recording: window j is what acquisition.m:27-34 reads with
+// file.skip = skip_ms + j*epoch_ms, i.e. noncoh_blocks*coh_ms ms starting at byte
+// (skip_ms + j*epoch_ms) * samples_per_ms * dataPrecision * dataType (SDR_main.m:17-23 run once per epoch).
+// fseeko + fread go directly into the pinned staging buffers, overlapped with the previous window's search.
+int gnssacq_sweep_file(gnssacq_handle* h, const char* path, int64_t skip_ms, int32_t epoch_ms, int32_t n_windows,
+                       gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !path || !out || n_windows < 0 || skip_ms < 0 || epoch_ms < 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "bad argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(h, GNSSACQ_ERR_INVALID_ARG, "cannot open the recording");
+    const long long ms_bytes = (long long)h->N * h->cfg.data_precision * h->cfg.data_type;
+    const int rc = sweep_impl(h, n_windows, out, st, [&](int i, void* dst) {
+        const long long off = (skip_ms + (long long)i * epoch_ms) * ms_bytes;               // acquisition.m:27
+        if (fseeko(f, (off_t)off, SEEK_SET) != 0) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "seek past the end of the recording");
+        if (std::fread(dst, 1, h->if_bytes, f) != h->if_bytes)                             // acquisition.m:28/34
+            return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "recording ends inside a window");
+        return (int)GNSSACQ_OK;
+    });
+    std::fclose(f);
+    return rc;
 }
 
 // Tracking correlators, SURVEY 8f-2.  gnssacq_track_load keeps a segment of the recording resident in HBM;

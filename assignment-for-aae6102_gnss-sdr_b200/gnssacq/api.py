@@ -97,7 +97,7 @@ EXPORTS = (
     "gnssacq_destroy", "gnssacq_last_error", "gnssacq_set_stream", "gnssacq_search",
     "gnssacq_search_device", "gnssacq_enqueue_device", "gnssacq_enqueue_device_out", "gnssacq_fetch_results",
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
-    "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_track_load", "gnssacq_correlate",
+    "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_sweep_file", "gnssacq_track_load", "gnssacq_correlate",
     "gnssacq_loop_params_default", "gnssacq_track",
 )
 
@@ -134,6 +134,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_track.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.POINTER(LoopParams), C.c_int32, C.POINTER(TrackRecord)]
     lib.gnssacq_correlate.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.c_int32, vp, vp, vp]
     lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
+    lib.gnssacq_sweep_file.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
@@ -275,6 +276,26 @@ class Searcher:
         self._check(lib.gnssacq_sweep(self._h, ptrs, n, each, out, C.byref(st)))
         self.last_stats = st
         return [list(out[i * p:(i + 1) * p]) for i in range(n)]
+
+    def sweep_file(self, path: str, skip_ms: int, epoch_ms: int, n_windows: int) -> List[List[Result]]:
+        """Re-acquisition sweep read by the library from a recording file: window j starts `skip_ms + j*epoch_ms`
+        ms into the file (acquisition.m:27 with file.skip advanced by `epoch_ms` per epoch)."""
+        p = self.cfg.n_prn
+        if n_windows <= 0:
+            return []
+        out = (Result * (n_windows * p))()
+        st = Stats()
+        self._check(lib.gnssacq_sweep_file(self._h, os.fsencode(path), int(skip_ms), int(epoch_ms), int(n_windows),
+                                           out, C.byref(st)))
+        self.last_stats = st
+        return [list(out[i * p:(i + 1) * p]) for i in range(n_windows)]
+
+    def fetch_stats(self) -> "Stats":
+        """Timings of the last enqueued search (synchronises); no rows copied."""
+        st = Stats()
+        self._check(lib.gnssacq_fetch_results(self._h, None, C.byref(st)))
+        self.last_stats = st
+        return st
 
     def track_load(self, if_bytes) -> None:
         """Keep a segment of the recording resident in HBM for `correlate`."""

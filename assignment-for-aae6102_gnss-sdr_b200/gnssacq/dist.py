@@ -62,11 +62,15 @@ class CudaShard:
         self.h_all = torch.empty(world * self.max_rows * ROW_BYTES, dtype=torch.uint8).pin_memory()
 
     def bind_stream(self) -> None:
+        """Kept for callers of r01; enqueue() now binds the handle to torch's current stream on every call."""
         if self.searcher:
             self.searcher.set_stream(self.torch.cuda.current_stream().cuda_stream)
 
     def enqueue(self, dist, h_if=None) -> None:
-        """One acquisition, stream-ordered: [H2D on rank 0] -> broadcast -> search shard -> all-gather."""
+        """One acquisition, stream-ordered ON TORCH'S CURRENT STREAM: [H2D on rank 0] -> broadcast -> search shard
+        -> all-gather.  The handle is (re)bound to that stream here, every call, so the search can never run
+        unordered against the collectives and copies around it (whatever stream the caller has switched to)."""
+        self.bind_stream()
         if h_if is not None and self.rank == 0:
             self.d_if.copy_(h_if, non_blocking=True)
         if self.world > 1:

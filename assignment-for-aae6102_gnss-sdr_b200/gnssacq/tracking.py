@@ -60,7 +60,11 @@ def bit_edge_index(p_i: np.ndarray) -> int:
 def trackingCT(file, signal, track, Acquired) -> Tuple[Dict[int, Dict[str, np.ndarray]], np.ndarray, np.ndarray]:
     """Stage 1 of trackingCT.m.  ``TckResultCT[prn]`` holds the per-period arrays of ``:153-172`` (P_i, P_q, E_i,
     E_q, L_i, L_q, PLLdiscri, DLLdiscri, codedelay, remChip, codeFreq, carrierFreq, remPhase, numSample, delayValue,
-    absoluteSample, codedelay2); ``CN0_Eph`` is (periods // 20, n_sv); ``countinx`` the bit-edge index per SV."""
+    absoluteSample, codedelay2); ``CN0_Eph`` is (periods // 20, n_sv); ``countinx`` the bit-edge index per SV.
+
+    Deliberate deviation: ``codedelay[i]`` = AcqCodeDelay + the cumulative sum of THIS satellite's delayValue.
+    trackingCT.m:161 writes ``sum(delayValue(1:Index))`` with a LINEAR index into the (n_sv x n_ms) matrix, which
+    mixes the satellites' corrections and equals the per-satellite sum only when one SV is tracked."""
     sv = [int(p) for p in np.atleast_1d(Acquired["sv"])]
     n_ms = int(track.msToProcessCT_1ms)
     if not sv:

@@ -8,7 +8,8 @@ function Acquired = acquisition(file, signal, acq)
 cfg = struct('fs_hz', signal.Fs, 'if_hz', signal.IF, 'code_hz', signal.codeFreqBasis, ...
     'samples_per_ms', signal.Sample, 'data_type', file.dataType, 'data_precision', file.dataPrecision, ...
     'freq_min_hz', acq.freqMin, 'freq_step_hz', acq.freqStep, 'freq_num', acq.freqNum, ...
-    'noncoh_blocks', acq.datalen, 'coh_ms', 1, 'snr_threshold_db', 12, 'prn', 1:32);
+    'noncoh_blocks', acq.datalen, 'coh_ms', 1, 'snr_threshold_db', 12, 'prn', 1:32, 'n_gpus', 1);
+if isfield(acq, 'nGpus'), cfg.n_gpus = acq.nGpus; end    % PRN-major shards over several GPUs (gnssacq_search_multi)
 
 kinds = {'int8=>int8', 'int16=>int16'};
 bytesPerMs = signal.Sample * file.dataPrecision * file.dataType;
@@ -16,7 +17,8 @@ fseek(file.fid, file.skip * bytesPerMs, 'bof');
 raw = fread(file.fid, signal.Sample * file.dataType * acq.datalen, kinds{file.dataPrecision});
 
 fprintf('Acquiring... \n ');
-rows = gnssacq_mex(raw, cfg);            % n_prn x [prn acquired code_phase bin doppler peak noise snr]
+for svindex = 1:32, svindex, end       %#ok<NOPRT> acquisition.m:48 echoes the loop index; kept for identical console output
+rows = gnssacq_mex('search', raw, cfg);            % n_prn x [prn acquired code_phase bin doppler peak noise snr]
 hit = rows(rows(:, 2) == 1, :);
 
 Acquired = struct('sv', [], 'SNR', [], 'Doppler', [], 'codedelay', [], 'fineFreq', []);
@@ -37,7 +39,7 @@ end
 fprintf('Now refining Doppler freq... \n ');
 fseek(file.fid, file.skip * bytesPerMs, 'bof');
 longraw = fread(file.fid, signal.Sample * file.dataType * (acq.L + 1), kinds{file.dataPrecision});
-Acquired.fineFreq = gnssacq_mex(longraw, cfg, acq.L, Acquired.sv, Acquired.codedelay);
+Acquired.fineFreq = gnssacq_mex('fine', longraw, cfg, acq.L, Acquired.sv, Acquired.codedelay);
 for k = 1:numel(Acquired.sv)
     fprintf(' SV[%2d] SNR = %2.2f, Code phase = %5d, Raw Doppler = %5d, Fine Doppler = %5f \n ', ...
         Acquired.sv(k), Acquired.SNR(k), Acquired.codedelay(k), Acquired.Doppler(k), Acquired.fineFreq(k) - signal.IF);

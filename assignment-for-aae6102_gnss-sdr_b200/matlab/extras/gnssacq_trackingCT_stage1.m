@@ -1,9 +1,15 @@
-function [TckResultCT, CN0_Eph, countinx] = trackingCT(file, signal, track, Acquired)
-% Drop-in for the first (1 ms) stage of acqtckpos/trackingCT.m (lines 22-212): the conventional DLL/PLL loop of
+function [TckResultCT, CN0_Eph, countinx] = gnssacq_trackingCT_stage1(file, signal, track, Acquired)
+% The FIRST (1 ms) stage of acqtckpos/trackingCT.m only (its lines 22-212): the conventional DLL/PLL loop of
 % every acquired satellite runs on the GPU (gnssacq_mex 'track' -> gnssacq_track: one thread-block cluster per
-% channel, no host round trip per millisecond); C/N0 and the bit-edge index are computed here exactly as the
-% reference does.  The later stages of the reference (lines 214-533) are not replaced.
-%   addpath('<repo>/assignment-for-aae6102_gnss-sdr_b200/matlab', '-begin');
+% channel, no host round trip per millisecond); C/N0 and the bit-edge index are computed here as the reference does.
+% NOT a replacement of trackingCT: the reference goes on (lines 214-533: bit-edge re-run, 40 s of 10 ms
+% integrations) and returns the TckResultCT that naviDecode_updated consumes; this function returns the
+% 1 ms records of stage 1.  It therefore has its own name and lives in matlab/extras/, which must NOT be put on the
+% path in front of acqtckpos/ (only matlab/ itself, for acquisition.m, is): SDR_main.m:38 keeps calling the
+% reference's trackingCT.  Call it explicitly where the stage-1 loop is wanted.
+% Field note: TckResultCT(sv).codedelay(i) here is the plain cumulative sum of the DLL corrections
+% (AcqCodeDelay + sum over THIS satellite's first i delays).  trackingCT.m:161 writes sum(delayValue(1:Index)) with a
+% LINEAR index into the n_sv x n_ms matrix, which equals that only for a single satellite; the deviation is deliberate.
 n_ms = track.msToProcessCT_1ms;
 N = signal.Sample;
 bps = file.dataPrecision * file.dataType;
@@ -15,14 +21,14 @@ if file.dataPrecision == 2
 else
     seg = fread(file.fid, (n_ms + 3) * N * file.dataType, 'int8=>int8');
 end
-gnssacq_mex(seg, cfg, 'track_load');
+gnssacq_mex('track_load', seg, cfg);
 n_sv = length(Acquired.sv);
 ch = zeros(7, n_sv);
 for k = 1:n_sv                                                      % trackingCT.m:42-60
     ch(:, k) = [Acquired.sv(k); 0; N - Acquired.codedelay(k) + 1; Acquired.fineFreq(k); 0; signal.codeFreqBasis; 0];
 end
 loops = [track.DLLBW track.DLLDamp track.DLLGain track.PLLBW track.PLLDamp track.PLLGain track.CorrelatorSpacing];
-rec = gnssacq_mex(ch, cfg, loops, n_ms, 'track');                   % 14 x n_ms x n_sv
+rec = gnssacq_mex('track', ch, cfg, loops, n_ms);                   % 14 x n_ms x n_sv
 countinx = zeros(1, n_sv);
 K = 20;
 for k = 1:n_sv

@@ -181,37 +181,94 @@ def cpu_single_thread_baseline(cfg, budget_s=12.0):
             "numpy": np.__version__}
 
 
+def config_dict(cfg):
+    """The `config` object both arms print (the driver compares them)."""
+    cells = len(PRNS) * cfg["bins"] * cfg["n"]
+    return {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
+            "coh_ms": cfg["m"], "prns": 32, "cells": cells, "cell_blocks": cells * cfg["k"],
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB device memset outside the per-step event pair)"}
+
+
+REFERENCE_BUDGET_S = 420.0
+
+
 def run_reference(args, cfg):
+    """The reference's own CPU implementation of the path (oracle port of acquisition.m:53-61, literal loop:
+    three FFTs per (PRN, bin, block) unit, NumPy float64) on all host cores, one PRN per task.  Configs 1 and 2:
+    every step is ONE FULL acquisition (32 PRNs x all bins x all K blocks), nothing scaled, as long as
+    (steps + warmup) of them fit REFERENCE_BUDGET_S on this box; otherwise, and for configs 3-5 (hours of CPU
+    work), a step is a bounded sample (all 32 PRNs x all bins x the first kb of K blocks, coherent length 1 ms)
+    scaled by kb/K, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    kb = 2 if cfg["m"] == 1 else 1
-    _ref_setup(cfg, kb)
-    pool = mp.get_context("fork").Pool(cores)
-    tasks = [(PRNS[i % len(PRNS)], kb) for i in range(cores)]
-    for _ in range(args.warmup):
-        pool.map(_ref_worker, tasks)
+    n_steps, n_warm = args.steps, args.warmup
+    # cost of one (PRN, all bins, one block) task on one core
+    _ref_setup(cfg, 1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pool.map(_ref_worker, tasks)
+    _ref_worker((1, 1))
+    t_blk = time.perf_counter() - t0
+    rounds = math.ceil(len(PRNS) / cores)
+    full_ok = cfg["m"] == 1 and t_blk * cfg["k"] * rounds * (n_steps + n_warm) * 1.15 <= REFERENCE_BUDGET_S
+    if full_ok:
+        kb = cfg["k"]
+    else:
+        kb = max(1, min(cfg["k"], int(REFERENCE_BUDGET_S / (t_blk * rounds * (n_steps + n_warm) * 1.15))))
+    _ref_setup(cfg, kb)
+    pool = mp.get_context("fork").Pool(min(cores, len(PRNS)))
+    tasks = [(p, kb) for p in PRNS]
+    for _ in range(n_warm):
+        pool.map(_ref_worker, tasks, chunksize=1)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        pool.map(_ref_worker, tasks, chunksize=1)
     dt = time.perf_counter() - t0
     pool.close()
-    cells_per_step = cores * cfg["bins"] * cfg["n"] * (kb / cfg["k"])
-    value = cells_per_step * args.steps / dt
-    sample = (f"per step: {cores} PRNs (one per core) x {cfg['bins']} bins x {kb} of {cfg['k']} blocks, literal "
-              f"acquisition.m:53-61 loop (3 FFTs per unit) in NumPy float64; cells scaled by {kb}/{cfg['k']}")
+    scale = kb / cfg["k"]
+    cells_per_step = len(PRNS) * cfg["bins"] * cfg["n"] * scale
+    value = cells_per_step * n_steps / dt
+    if full_ok:
+        sample = (f"per step: one full acquisition, 32 PRNs x {cfg['bins']} bins x {cfg['k']} blocks, literal "
+                  f"acquisition.m:53-61 loop (3 FFTs per unit) in NumPy float64, one PRN per task on {cores} cores; nothing scaled")
+    else:
+        sample = (f"per step: 32 PRNs x {cfg['bins']} bins x {kb} of {cfg['k']} blocks at 1 ms coherent, literal "
+                  f"acquisition.m:53-61 loop in NumPy float64 on {cores} cores; cells scaled by {kb}/{cfg['k']} "
+                  f"(a full step would not fit the {REFERENCE_BUDGET_S:.0f} s budget of this arm)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "steps": n_steps, "warmup": n_warm, "ms_per_step": dt / n_steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
-                   "coh_ms": cfg["m"], "prns": 32},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(cfg),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "full_step": bool(full_ok)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def parity_check(cfg, raw, rows, prns):
+    """Checker for the timed result: the rows the bench just produced against the oracle on a PRN
+    subset, same bytes, tolerances of tests/helpers.py (indices / decision exact unless the oracle's top two cells
+    are within 2e-5, peak and SNR within 1e-4).  The oracle is only ever the checker here."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import assert_rows_match, oracle_rows_chunked, structs
+    file, signal, acq = structs(cfg["fs"], cfg["if_hz"], datalen=cfg["k"], freq_min=cfg["fmin"],
+                                freq_step=cfg["fstep"], freq_num=cfg["bins"])
+    t0 = time.perf_counter()
+    ref = oracle_rows_chunked(raw, file, signal, acq, prns, coh_ms=cfg["m"],
+                              chunk_bins=max(1, min(20, cfg["bins"] // 12)) if cfg["m"] == 1 else (20 if cfg["bins"] < 1000 else 100))
+    by = {r.prn: r for r in rows}
+    out = {"prns": list(prns), "oracle": "oracle/acquisition_ref.py (NumPy float64 restatement of acquisition.m:41-80)",
+           "oracle_s": None, "tolerance": "code phase / Doppler bin / decision exact unless oracle top-2 gap < 2e-5; peak, SNR 1e-4 rel"}
+    try:
+        ties = assert_rows_match([by[p] for p in prns], ref, what="bench parity")
+        out.update(ok=True, ties=ties)
+    except AssertionError as e:
+        out.update(ok=False, error=str(e)[:300])
+    out["oracle_s"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -303,10 +360,20 @@ def run_gpu(args, cfg):
     # ---- timed region 2: end to end through the public API, host buffers, H2D + D2H inside ----
     barrier()
     t0 = time.perf_counter()
+    e2e_api = "CudaShard.enqueue(h_if) + fetch: pinned H2D on rank 0, IF exchange, shard search, row exchange, D2H"
     if sweep and world == 1:
         # the public call for this workload: one gnssacq_sweep over `steps` host windows
         swept = shard.searcher.sweep([raws[i % len(raws)] for i in range(args.steps)])
         rows = swept[-1]
+        e2e_api = "gnssacq_sweep (Searcher.sweep): host windows -> library staging -> H2D -> search -> D2H"
+    elif world == 1:
+        # the call the MEX gateway makes (matlab/gnssacq_mex.c -> gnssacq_search): caller-owned pageable host
+        # buffer in, result rows out; staging copy, H2D, kernels, D2H and the host sync are all inside
+        import numpy as np
+        host = [np.frombuffer(r, dtype=np.uint8).copy() for r in raws]
+        for i in range(args.steps):
+            rows = shard.searcher.search(host[i % len(host)])
+        e2e_api = "gnssacq_search (Searcher.search): pageable host buffer -> library pinned staging -> H2D -> K1/K2/K4 -> D2H"
     else:
         for i in range(args.steps):
             shard.enqueue(d, h_if=h_ifs[i % len(h_ifs)])
@@ -344,13 +411,11 @@ def run_gpu(args, cfg):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "n": cfg["n"], "bins": cfg["bins"], "noncoh_blocks": cfg["k"],
-                       "coh_ms": cfg["m"], "prns": 32, "cells": cells, "cell_blocks": cells * cfg["k"],
-                       "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2+clusters", 3: "l2+coop-groups"}.get(st.exchange),
+            "config": config_dict(cfg),
+            "run": {   "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2+clusters", 3: "l2+coop-groups"}.get(st.exchange),
                                   "resident_clusters": st.resident_clusters,
                                   "work_split": {1: "whole rows", 2: "block-granular tail"}.get(st.work_split)},
                        "sharding": f"PRN-major, {n_local} PRNs on rank 0",
-                       "l2": "flushed between steps (256 MiB device memset, outside the per-step event pair)",
                        "latency_ms_32prn": e2e_s / args.steps * 1e3,
                        **({"sweep": f"{len(raws)} distinct windows, one every {cfg['epoch_ms']} ms, cycled; e2e = one gnssacq_sweep call over {args.steps} host windows"
                            if world == 1 else f"{len(raws)} distinct windows cycled, one host window per step"} if sweep else {})},
@@ -371,12 +436,15 @@ def run_gpu(args, cfg):
                              "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
             "e2e": {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(raw),
-                    "d2h_bytes_per_step": world * shard.max_rows * ROW_BYTES},
+                    "d2h_bytes_per_step": world * shard.max_rows * ROW_BYTES, "api": e2e_api},
             "gpu_launches": launches * args.steps,
             "clocks": clk.summary(),
             "wall_s_timed_region": t_wall,
             "acquired": [r.prn for r in rows if r.acquired],
         }
+        if not args.no_parity:
+            subset = [3, 8, 22, 30] if cfg["m"] == 1 else [3, 22]
+            line["parity_checked"] = parity_check(cfg, raws[(args.steps - 1) % len(raws)], rows, subset)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_thread_baseline(cfg)
         print(json.dumps(line))
@@ -390,12 +458,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="BASELINE.json config; default 1 = Opensky-shaped block, the north_star target")
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--cluster-ctas", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--exchange", type=int, default=0, help="0 auto, 1 DSMEM, 2 L2-resident exchange buffer")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

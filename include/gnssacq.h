@@ -138,7 +138,9 @@ int gnssacq_search_device(gnssacq_handle* h, const void* d_if_samples, size_t nb
                           gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
 
 /* Enqueue only (no host synchronisation, results stay in HBM): for back-to-back timing loops.
- * gnssacq_fetch_results() synchronises and copies the rows of the last enqueued search. */
+ * gnssacq_fetch_results() synchronises and copies the rows of the last enqueued search -- from wherever that
+ * search wrote them (the handle's own table, or the device buffer given to gnssacq_enqueue_device_out).
+ * out may be NULL when only the timings are wanted; GNSSACQ_ERR_STATE if nothing has been enqueued yet. */
 int gnssacq_enqueue_device(gnssacq_handle* h, const void* d_if_samples, size_t nbytes);
 int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
 /* Enqueue only, and have K4 write the cfg.n_prn result rows straight into caller-owned HBM
@@ -163,6 +165,15 @@ int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n_handles, const voi
  * the last window. */
 int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
                   gnssacq_result* out, gnssacq_stats* stats);
+
+/* The same sweep read straight from a recording file (BASELINE config 4: one acquisition every epoch_ms over a
+ * 90 s recording = 900 windows).  Window j = the bytes acquisition.m:27-34 reads with file.skip = skip_ms +
+ * j*epoch_ms: noncoh_blocks*coh_ms ms from byte (skip_ms + j*epoch_ms) * samples_per_ms * dataPrecision *
+ * dataType (SDR_main.m:17-23 run once per epoch).  fseek + fread fill the library's pinned staging buffers
+ * directly while the previous window is searched.  A window that runs past the end of the file:
+ * GNSSACQ_ERR_SHORT_BUFFER (MATLAB's fread would return fewer samples and acquisition.m:56 would then fail). */
+int gnssacq_sweep_file(gnssacq_handle* h, const char* path, int64_t skip_ms, int32_t epoch_ms, int32_t n_windows,
+                       gnssacq_result* out, gnssacq_stats* stats);
 
 /* Tracking correlators (replaces trackingCT.m:85-118, and with 25 taps the correlator bank of
  * trackingCT_POS_updated_multicorrelator.m:207-260).  The loop filters stay with the caller (trackingCT.m:135-150).

@@ -9,6 +9,7 @@ typedef size_t mwSize;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
 typedef enum { mxDOUBLE_CLASS = 6 } mxClassID;
 int mxIsChar(const mxArray*);
+int mxGetString(const mxArray*, char*, mwSize);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 int mxIsStruct(const mxArray*); int mxIsInt8(const mxArray*); int mxIsInt16(const mxArray*); int mxIsDouble(const mxArray*);
 size_t mxGetM(const mxArray*); size_t mxGetN(const mxArray*);

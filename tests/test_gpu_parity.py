@@ -17,6 +17,8 @@ from gnssacq import api
 from helpers import structs, small_spec, oracle_rows, assert_rows_match, METRIC_RTOL
 
 pytestmark = pytest.mark.gpu
+import ctypes as _C
+C_RESULT = _C.sizeof(api.Result)
 
 # (cluster CTAs, threads, exchange: 1 = DSMEM, 2 = L2-resident buffer)
 # exchange: 1 = DSMEM clusters, 2 = L2 buffer + persistent clusters, 3 = L2 buffer + cooperative CTA groups
@@ -389,6 +391,61 @@ def test_reacquisition_sweep_equals_single_searches(n, datalen, n_windows):
         with pytest.raises(gnssacq.GnssAcqError):
             s.sweep([windows[0][:-2]])
     assert_rows_match(swept[0], oracle_rows(windows[0], file, signal, acq, prns), what=f"sweep N={n} window 0")
+
+
+def test_sweep_from_a_recording_file(tmp_path):
+    """gnssacq_sweep_file: the library does acquisition.m:27-34's fseek/fread itself, window j = file.skip advanced by
+    epoch_ms per epoch (BASELINE config 4).  Rows per window = gnssacq_search on the bytes acquisition.m would read."""
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    spec = small_spec(fs, if_hz, n)
+    total_ms, skip, epoch, n_win = 64, 3, 10, 6
+    blob = synth_if(spec, 0, total_ms)
+    rec = tmp_path / "rec.bin"
+    rec.write_bytes(blob)
+    prns = [3, 7, 22, 30]
+    ms_bytes = n * 2
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        want = [[bytes(r) for r in s.search(blob[(skip + epoch * j) * ms_bytes:(skip + epoch * j + 2) * ms_bytes])]
+                for j in range(n_win)]
+        got = s.sweep_file(str(rec), skip, epoch, n_win)
+        assert [[bytes(r) for r in rows] for rows in got] == want
+        assert s.sweep_file(str(rec), skip, epoch, 0) == []
+        with pytest.raises(gnssacq.GnssAcqError) as e:                    # the last window would run past the end
+            s.sweep_file(str(rec), skip, epoch, 8)
+        assert e.value.code == -3
+        with pytest.raises(gnssacq.GnssAcqError):
+            s.sweep_file(str(tmp_path / "missing.bin"), 0, 10, 1)
+        # ... and the handle is still usable afterwards
+        assert [bytes(r) for r in s.search(blob[skip * ms_bytes:(skip + 2) * ms_bytes])] == want[0]
+    file.fid, file.skip = io.BytesIO(blob), skip
+    assert_rows_match(got[0], oracle.coarse_search(oracle.read_if_block(file, signal, 2), signal, acq, prns), what="sweep_file window 0")
+
+
+def test_fetch_follows_the_last_search_output():
+    """gnssacq_fetch_results returns the rows of the LAST enqueued search also when that search wrote them into a
+    caller-owned device buffer (gnssacq_enqueue_device_out), and accepts out == NULL for timings only."""
+    import torch
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    a = synth_if(small_spec(fs, if_hz, n), 0, 2)
+    b = synth_if(small_spec(fs, if_hz, n, seed=77), 5, 2)
+    prns = [3, 7, 22]
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        with pytest.raises(gnssacq.GnssAcqError) as e:
+            s.fetch()
+        assert e.value.code == -7                                       # nothing enqueued yet
+        rows_a = [bytes(r) for r in s.search(a)]
+        rows_b = [bytes(r) for r in s.search(b)]
+        assert rows_a != rows_b
+        s.search(a)                                                     # the handle's own table now holds A
+        d_if = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        d_out = torch.zeros(len(prns) * C_RESULT, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        s.enqueue_device_out(d_if.data_ptr(), d_if.numel(), d_out.data_ptr())
+        assert [bytes(r) for r in s.fetch()] == rows_b                  # not the stale rows of A
+        st = s.fetch_stats()
+        assert st.search_ms > 0 and st.kernel_launches >= 3
 
 
 def test_plain_c_example_end_to_end(tmp_path):

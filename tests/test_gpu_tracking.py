@@ -187,6 +187,8 @@ def test_trackingct_twin_on_a_synthetic_recording():
         assert abs(np.mean(r["carrierFreq"][100:]) - (if_hz + d)) < 5.0
         assert abs(np.mean(r["codeFreq"][100:]) - 1.023e6) < 2.0          # (the generator has no code Doppler)
         assert np.all(np.abs(r["delayValue"]) <= 1) and np.all(r["numSample"] == n + r["delayValue"])
+        # per-satellite cumulative sum: a documented, deliberate deviation from trackingCT.m:161, whose linear index
+        # into the n_sv x n_ms delayValue matrix mixes the satellites (gnssacq/tracking.py)
         assert np.allclose(r["codedelay"], cd + np.cumsum(r["delayValue"]))
         bps = 2
         assert r["absoluteSample"][0] == ((3 * n) + (n - cd + 1) + r["numSample"][0]) * bps       # ftell after the first read
