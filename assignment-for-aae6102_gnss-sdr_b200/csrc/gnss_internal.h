@@ -23,7 +23,9 @@ struct SearchArgs {
     const int* bin_shift;  // [B] shift in FFT bins relative to that base
     int P, B, K;
     int w;                 // ceil(Fs/fc) (acquisition.m:66)
-    Candidate* cand;       // [P][B]
+    Candidate* cand;       // [P][cand_stride]: row (p, b) at cand[p*cand_stride + b].  A shard of a multi-GPU search
+                           // points this straight into the ROOT GPU's table (peer memory, NVLink stores)
+    int cand_stride;       // >= B (the full grid's bin count when the handle owns a bin sub-range)
     float* surface;        // optional [P][B][N] (debug), lag order
     cf* scratch;           // L2-exchange variants: [groups][2][16][RS] (double-buffered finished rows)
     unsigned* group_ctr;   // coop variant: one arrival counter per CTA group (zeroed before the launch)
@@ -44,6 +46,21 @@ struct WipeArgs {
     double fs_hz;
     const double* means;   // [2] int16 path (device), else nullptr
     cf* x;                 // [n_bases][K][N]
+};
+
+// K1 v2 (r02): the IF block is first re-ordered by `comb_kernel` into 16 "comb" rows per millisecond --
+// row rho of ms t holds samples n = 16*m + rho, m = 0 .. N/16-1, contiguously (pitch bytes per row, a multiple
+// of 16) -- because an a-row of the prime-factor array only ever reads samples of ONE residue n mod 16
+// (n = a*M1 + b*M2 + c*M3 with M2, M3 multiples of 16).  wipe2_kernel then stages exactly its rows with
+// cp.async (contiguous 16-byte chunks) instead of gathering single bytes scattered over the whole block.
+struct Wipe2Args {
+    const unsigned char* comb;    // [K*M ms][16][pitch] bytes
+    int pitch;                    // bytes per comb row (multiple of 16)
+    int bps;                      // bytes per sample: 1 int8 real, 2 int8 I/Q, 4 int16 I/Q
+    int coh_ms, K;
+    const double* base_w;         // [n_bases] (IF + doppler) / Fs of each base, cycles per sample
+    const double* means;          // [2] int16 path (device), else nullptr
+    cf* x;                        // [n_bases][K][NX]
 };
 
 struct CodeArgs {
@@ -74,6 +91,8 @@ struct VariantOps {
     cudaError_t (*prepare)();
     cudaError_t (*launch_code)(const CodeArgs&, int units, cudaStream_t);
     cudaError_t (*launch_wipe)(const WipeArgs&, int units, cudaStream_t);
+    cudaError_t (*launch_wipe2)(const Wipe2Args&, int units, cudaStream_t);
+    size_t (*smem_wipe2)(int pitch, int coh_ms);
     cudaError_t (*launch_natural)(const NaturalArgs&, int units, cudaStream_t);
     cudaError_t (*launch_fine)(const FineArgs&, int units, cudaStream_t);
     cudaError_t (*launch_search)(const SearchArgs&, int rows, cudaStream_t);

@@ -225,6 +225,107 @@ __global__ void __launch_bounds__(T, MINB) wipe_kernel(WipeArgs a) {
     unit_device<Q, R, T>(ld, st, D, Dall, tw, rank, tid);
 }
 
+// ---- K1 v2: wipe-off (+ M-ms fold) + forward FFT with cp.async-staged comb rows (acquisition.m:56-57) ----
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// residue n mod 16 of every sample an a-row reads (M2 and M3 are multiples of 16)
+template <int Q>
+GNSS_HD int comb_row_of(int a) { return (a * (Geo<Q>::M1 % 16)) % 16; }
+
+template <int Q, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) wipe2_kernel(Wipe2Args a) {
+    GNSS_KERNEL_PROLOGUE
+    Tw4* tw = reinterpret_cast<Tw4*>(D + S::D_ELEMS);
+    unsigned char* stage = reinterpret_cast<unsigned char*>(tw + 100);          // [2 buffers][A rows][pitch]
+    fill_tw125(tw, tid, T);
+    const int base = unit / a.K, k = unit - base * a.K;
+    const double w = a.base_w[base];
+    const float mean_i = a.means ? (float)a.means[0] : 0.f, mean_q = a.means ? (float)a.means[1] : 0.f;
+    const int pitch = a.pitch, bps = a.bps, M = a.coh_ms;
+    // stage ms j of this coherent block: rows rho(a) of the CTA's A a-rows, 16-byte chunks, all threads
+    auto stage_ms = [&](int j, int buf) {
+        const int chunks = pitch >> 4;
+        for (int i = tid; i < S::A * chunks; i += T) {
+            const int al = i / chunks, ch = i - al * chunks;
+            const int rho = comb_row_of<Q>(rank * S::A + al);
+            const unsigned char* src = a.comb + ((size_t)((size_t)k * M + j) * 16 + rho) * pitch + (size_t)ch * 16;
+            cp_async16(stage + ((size_t)buf * S::A + al) * pitch + (size_t)ch * 16, src);
+        }
+        cp_async_commit();
+    };
+    // steps s = round * M + j; step s reads buffer s & 1 while step s + 1 is being staged into the other one
+    // (M == 1: a single buffer, staged once, serves every round)
+    constexpr int ROUNDS = (S::P1_TASKS + T - 1) / T;
+    const int n_steps = (M > 1) ? ROUNDS * M : 1;
+    stage_ms(0, 0);
+    int step = 0;
+    for (int t0 = 0; t0 < S::P1_TASKS; t0 += T) {
+        const int task = t0 + tid;
+        const bool has = task < S::P1_TASKS;
+        const int al = has ? task / 125 : 0, b = has ? task - al * 125 : 0;
+        const int arow = rank * S::A + al;
+        cf z[Q];
+        static_for<0, Q>([&](auto c_) { z[decltype(c_)::value] = mk(0.f, 0.f); });
+        for (int j = 0; j < M; ++j) {
+            const int buf = (M > 1) ? (step & 1) : 0;
+            if (M > 1 || t0 == 0) {
+                if (step + 1 < n_steps) { stage_ms((j + 1) % M, buf ^ 1); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncthreads();                         // everybody's chunks of this step have landed
+            }
+            if (has) {
+                const unsigned char* row = stage + ((size_t)buf * S::A + al) * pitch;
+                static_for<0, Q>([&](auto c_) {
+                    constexpr int C = decltype(c_)::value;
+                    const int n = Geo<Q>::good(arow, b, C);
+                    const int m = n >> 4;                 // position in the comb row (n = 16 m + rho)
+                    float xi, xq;
+                    if (bps == 2) {
+                        const unsigned short v = *reinterpret_cast<const unsigned short*>(row + 2 * m);
+                        xi = (float)(signed char)(v & 0xff);
+                        xq = (float)(signed char)(v >> 8);
+                    } else if (bps == 4) {
+                        const unsigned v = *reinterpret_cast<const unsigned*>(row + 4 * m);
+                        xi = (float)(short)(v & 0xffff) - mean_i;
+                        xq = (float)(short)(v >> 16) - mean_q;
+                    } else {
+                        xi = (float)(signed char)row[m];
+                        xq = 0.f;
+                    }
+                    // acquisition.m:43: exp(i*2*pi*f*n1/Fs), n1 = 1-based index inside the coherent block
+                    const double cyc = w * (double)((long long)j * Geo<Q>::N + n + 1);
+                    const float fr = (float)(cyc - floor(cyc));
+                    float si, co;
+                    sincospif(2.0f * fr, &si, &co);
+                    z[C].x += xi * co - xq * si;
+                    z[C].y += xi * si + xq * co;
+                });
+            }
+            if (M > 1) __syncthreads();                  // this buffer is the target of the next-but-one staging
+            ++step;
+        }
+        if (has) {
+            dft_odd<Q>(z);
+            pass1_store<Q, R>(task, z, D);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    pass2_all<Q, R, T>(D, tw, tid);
+    __syncthreads();
+    pass3_all<Q, R, T>(D, tw, tid);
+    cl_sync<R>();
+    SpectrumStorer st{a.x + (size_t)unit * G::NX, 1.0f, 0, 1};
+    for (int t = tid; t < S::P4_TASKS; t += T) pass4_task<Q, R>(t, rank, Dall, st);
+    cl_sync<R>();
+}
+
 template <int Q, int R, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) natural_kernel(NaturalArgs a) {
     GNSS_KERNEL_PROLOGUE
@@ -347,7 +448,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel(SearchArgs a) {
         c.lag = rs->g_lag;
         c.sum_all = s_all;
         c.sum_win = s_win;
-        a.cand[(size_t)p * a.B + b] = c;
+        a.cand[(size_t)p * a.cand_stride + b] = c;
     }
     if constexpr (R > 1) cluster.sync();   // keep every CTA's shared memory alive until rank 0 has read it
 }
@@ -481,7 +582,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_l2x(SearchArgs a) {
             c.lag = rs->g_lag;
             c.sum_all = s_all;
             c.sum_win = s_win;
-            a.cand[(size_t)p * a.B + b] = c;
+            a.cand[(size_t)p * a.cand_stride + b] = c;
         }
         if constexpr (R > 1) cluster.sync(); else __syncthreads();   // slots are rewritten by the next row
     }
@@ -821,7 +922,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
                     c.lag = rs->g_lag;
                     c.sum_all = s_all;
                     c.sum_win = s_win;
-                    a.cand[(size_t)p * a.B + b] = c;
+                    a.cand[(size_t)p * a.cand_stride + b] = c;
                 }
             }
             __syncthreads();
@@ -870,6 +971,8 @@ struct Variant {
         e = cudaFuncSetAttribute(code_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(wipe_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(wipe2_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(natural_kernel<Q, RT, TT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<Q, RT>::transform);
         if (e != cudaSuccess) return e;
@@ -921,6 +1024,12 @@ struct Variant {
     static cudaError_t launch_wipe(const WipeArgs& a, int units, cudaStream_t s) {
         return launch_clustered(wipe_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
+    static size_t smem_wipe2(int pitch, int coh_ms) {
+        return Smem<Q, RT>::transform + (size_t)(coh_ms > 1 ? 2 : 1) * Split<Q, RT>::A * (size_t)pitch;
+    }
+    static cudaError_t launch_wipe2(const Wipe2Args& a, int units, cudaStream_t s) {
+        return launch_clustered(wipe2_kernel<Q, RT, TT, MT>, a, units, RT, TT, smem_wipe2(a.pitch, a.coh_ms), s);
+    }
     static cudaError_t launch_natural(const NaturalArgs& a, int units, cudaStream_t s) {
         return launch_clustered(natural_kernel<Q, RT, TT, MT>, a, units, RT, TT, Smem<Q, RT>::transform, s);
     }
@@ -933,7 +1042,7 @@ struct Variant {
     }
     static constexpr VariantOps ops() {
         return VariantOps{Q, R, T, Smem<Q, R>::search, Smem<Q, RT>::transform,
-                          &prepare, &launch_code, &launch_wipe, &launch_natural, &launch_fine, &launch_search,
+                          &prepare, &launch_code, &launch_wipe, &launch_wipe2, &smem_wipe2, &launch_natural, &launch_fine, &launch_search,
                           &launch_search_l2x, &max_clusters_l2x,
                           (size_t)2 * 16 * (Split<Q, R>::RS > GeoX<Q>::RSX ? Split<Q, R>::RS : GeoX<Q>::RSX) * sizeof(cf),
                           &launch_search_coop, &max_groups_coop,

@@ -68,10 +68,10 @@ void code_replica(const gnssacq_config& c, int prn, int8_t* out) {
 // K4: acquisition.m:62-70 from the per-row candidates.
 __global__ void finalize_kernel(const Candidate* __restrict__ cand, int P, int B, int N, int w, double fmin,
                                 double fstep, double thr, const int* __restrict__ prn_ids,
-                                gnssacq_result* __restrict__ out) {
+                                gnssacq_result* __restrict__ out, int cand_stride, int bin0) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const Candidate* row = cand + (size_t)p * B;
+    const Candidate* row = cand + (size_t)p * cand_stride;
     float g = -1.f;
     for (int b = 0; b < B; ++b) g = fmaxf(g, row[b].peak);
     int fbin = -1, cp = INT_MAX;
@@ -92,13 +92,85 @@ __global__ void finalize_kernel(const Candidate* __restrict__ cand, int P, int B
     r.prn = prn_ids[p];
     r.acquired = (snr >= thr) ? 1 : 0;                  // :70 (NaN compares false)
     r.code_phase = cp;
-    r.doppler_bin = fbin;
-    r.doppler_hz = fmin + fstep * (double)fbin;         // :64
+    r.doppler_bin = bin0 + fbin;                        // index in the full grid (bin0 != 0: the handle owns a bin range)
+    r.doppler_hz = fmin + fstep * (double)(bin0 + fbin);   // :64
     r.peak = pk;
     r.noise_meansq = noise;
     r.snr_db = snr;
     r.fine_freq_hz = nan("");
     out[p] = r;
+}
+
+// K1a (r02): re-order the raw IF block (acquisition.m:27-38's bytes, as read) into 16 comb rows per millisecond:
+// out[ms][rho][m] = sample 16*m + rho of that ms (see Wipe2Args).  Input is read with 16-byte vector loads
+// (8 packed int8 I/Q samples per load, fully coalesced) -- `raw` may be a PEER pointer: on ranks > 0 of a
+// multi-GPU search this kernel is what pulls the IF block out of rank 0's HBM over NVLink, so no separate
+// broadcast is needed.  A CTA handles TM consecutive m of one ms (TM*16 samples, contiguous in the input).
+constexpr int kCombTM = 256;
+// Flags of the multi-GPU exchange live in the ROOT GPU's memory; other GPUs read / write them over NVLink.
+__device__ __forceinline__ void flag_store_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned flag_load_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= epoch (wrap-safe); gives up after ~4 s of GPU clock and records it in *timeout (never hangs a box)
+__device__ __forceinline__ void flag_wait_sys(const unsigned* p, unsigned epoch, unsigned* timeout) {
+    const long long t0 = clock64();
+    while ((int)(flag_load_sys(p) - epoch) < 0) {
+        if (clock64() - t0 > 8000000000ll) { if (timeout) atomicExch(timeout, 1u); break; }
+        __nanosleep(200);
+    }
+}
+__global__ void __launch_bounds__(256) comb_kernel(const unsigned char* __restrict__ raw, unsigned char* __restrict__ out,
+                                                   int rows_per_ms /* N/16 */, int bps, int pitch, int tiles_per_ms,
+                                                   unsigned* flag_publish, const unsigned* flag_wait, unsigned epoch,
+                                                   unsigned* timeout) {
+    extern __shared__ __align__(16) unsigned smem_w[];       // [TM][4*bps + 1] words (one pad word per m: conflict-free column reads)
+    // multi-GPU: the root announces that its IF buffer holds this step's block (it does, by stream order);
+    // every other shard waits for that before pulling the block out of the root's HBM
+    if (flag_publish && blockIdx.x == 0 && threadIdx.x == 0) flag_store_sys(flag_publish, epoch);
+    if (flag_wait) {
+        if (threadIdx.x == 0) flag_wait_sys(flag_wait, epoch, timeout);
+        __syncthreads();
+    }
+    const int ms = blockIdx.x / tiles_per_ms, tile = blockIdx.x - ms * tiles_per_ms;
+    const int m0 = tile * kCombTM, tm = min(kCombTM, rows_per_ms - m0);
+    const int W = 4 * bps;                                    // words per m (16 samples)
+    const uint4* src = reinterpret_cast<const uint4*>(raw + ((size_t)ms * rows_per_ms + m0) * 16 * bps);
+    const int n_vec = tm * bps;                               // uint4 per tile: tm * 16 * bps / 16
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+        const uint4 v = src[i];
+        const int m = i / bps, part = i - m * bps;            // `bps` uint4 per m
+        unsigned* d = smem_w + m * (W + 1) + part * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(smem_w);
+    for (int e = threadIdx.x; e < 16 * tm; e += blockDim.x) {
+        const int rho = e / tm, m = e - rho * tm;
+        const unsigned char* p = sb + (size_t)m * (W + 1) * 4 + rho * bps;
+        unsigned char* q = out + ((size_t)ms * 16 + rho) * pitch + (size_t)(m0 + m) * bps;
+        if (bps == 2) *reinterpret_cast<unsigned short*>(q) = *reinterpret_cast<const unsigned short*>(p);
+        else if (bps == 4) *reinterpret_cast<unsigned*>(q) = *reinterpret_cast<const unsigned*>(p);
+        else *q = *p;
+    }
+}
+
+// non-root shard, after K2: its candidates are in the root's table (stores issued by the preceding kernel)
+__global__ void xchg_done_kernel(unsigned* flag, unsigned epoch) {
+    __threadfence_system();
+    flag_store_sys(flag, epoch);
+}
+// root, before K4: every other shard has delivered this step's candidates
+__global__ void xchg_wait_kernel(const unsigned* done_flags, int world, int n_prn, int n_bins, unsigned epoch, unsigned* timeout) {
+    const int r = 1 + (int)threadIdx.x;
+    if (r >= world) return;
+    // gnssacq_shard_plan: with fewer PRNs than shards the bins are split, and a shard may end up with none
+    const bool has_rows = n_prn >= world || n_bins / world > 0 || r < n_bins % world;
+    if (has_rows) flag_wait_sys(done_flags + r, epoch, timeout);
 }
 
 // acquisition.m:30-32 -- per-component mean of the int16 I/Q block (exact integer sums).
@@ -514,6 +586,9 @@ struct gnssacq_handle {
     cf* d_x = nullptr;
     int *d_bin_base = nullptr, *d_bin_shift = nullptr, *d_prn = nullptr;
     double* d_base_freq = nullptr;
+    double* d_base_w = nullptr;            // (IF + doppler) / Fs per base, cycles per sample (K1 v2)
+    unsigned char* d_comb = nullptr;       // [K*M ms][16][comb_pitch] re-ordered IF block (K1 v2), nullptr: K1 v1
+    int comb_pitch = 0;
     Candidate* d_cand = nullptr;
     gnssacq_result* d_res = nullptr;
     float* d_surface = nullptr;
@@ -521,6 +596,22 @@ struct gnssacq_handle {
     int l2x_clusters = 0;          // > 0: use the L2-exchange persistent search kernel with this many clusters
     int coop_groups = 0;           // > 0: use the cluster-free cooperative kernel with this many CTA groups
     unsigned* d_group_ctr = nullptr;
+    int bin0 = 0, B_full = 0;      // this handle's bins are [bin0, bin0 + B) of the B_full-bin grid
+    // multi-GPU exchange (gnssacq_xchg_*)
+    struct Xchg {
+        bool on = false, is_root = false;
+        gnssacq_shard sh{};
+        unsigned char* block = nullptr;        // root: the exchange block (cudaMalloc); others: the mapped root block
+        bool ipc_opened = false;
+        unsigned char* if_buf = nullptr;       // root's IF buffer
+        Candidate* cand_all = nullptr;         // root's [n_prn_total][freq_num_total]
+        unsigned* flags = nullptr;             // [0] IF ready, [1 + r] shard r done, [63] timeout
+        int* d_prn_all = nullptr;              // root
+        gnssacq_result* d_res_all = nullptr;   // root
+        gnssacq_result* h_res_all = nullptr;   // root, pinned
+        unsigned epoch = 0;
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    } xc;
     const gnssacq_result* d_last_rows = nullptr;   // where the last enqueued search wrote its rows (d_res or the caller's buffer)
     Candidate* d_row_slots = nullptr;
     float* d_partial = nullptr;    // cooperative kernel: accumulators of row parts handed between groups
@@ -630,6 +721,8 @@ int validate(const gnssacq_config* c, std::string& why) {
     if (c->n_prn < 1 || c->n_prn > GNSSACQ_MAX_PRN) { why = "n_prn must be 1..64"; return GNSSACQ_ERR_INVALID_ARG; }
     for (int i = 0; i < c->n_prn; ++i)
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
+    if (c->bin_count < 0 || c->bin_first < 0 || (c->bin_count > 0 && c->bin_first + c->bin_count > c->freq_num) ||
+        (c->bin_count == 0 && c->bin_first != 0)) { why = "bin_first / bin_count outside the freq_num grid"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->work_split < 0 || c->work_split > 2) { why = "work_split must be 0 (auto), 1 (whole rows) or 2 (block-granular tail)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->exchange < 0 || c->exchange > 3) { why = "exchange must be 0 (auto), 1 (DSMEM), 2 (L2 + clusters) or 3 (L2 + cooperative groups)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
@@ -692,8 +785,13 @@ int gnssacq_destroy(gnssacq_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_if); cudaFree(h->d_scode); cudaFree(h->d_cc); cudaFree(h->d_x);
-    cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq);
+    cudaFree(h->d_bin_base); cudaFree(h->d_bin_shift); cudaFree(h->d_prn); cudaFree(h->d_base_freq); cudaFree(h->d_base_w); cudaFree(h->d_comb);
     cudaFree(h->d_cand); cudaFree(h->d_res); cudaFree(h->d_surface); cudaFree(h->d_scratch); cudaFree(h->d_group_ctr); cudaFree(h->d_row_slots); cudaFree(h->d_partial); cudaFree(h->d_if2); cudaFree(h->d_res_sweep);
+    if (h->xc.on) {
+        if (h->xc.is_root) { cudaFree(h->xc.block); cudaFree(h->xc.d_prn_all); cudaFree(h->xc.d_res_all); if (h->xc.h_res_all) cudaFreeHost(h->xc.h_res_all); }
+        else if (h->xc.ipc_opened) cudaIpcCloseMemHandle(h->xc.block);
+        for (cudaEvent_t e : {h->xc.ev_a, h->xc.ev_b, h->xc.ev_c, h->xc.ev_d}) if (e) cudaEventDestroy(e);
+    }
     if (h->h_if2) cudaFreeHost(h->h_if2);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& e : h->ev_copied) if (e) cudaEventDestroy(e);
@@ -757,7 +855,16 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     h->M = cfg->coh_ms;
     h->w = (int)std::ceil(cfg->fs_hz / cfg->code_hz);          // acquisition.m:66
     h->if_bytes = gnssacq_if_bytes(cfg);
-    plan_bins(h);
+    plan_bins(h);                                               // on the FULL grid: same bases for every bin range
+    h->B_full = cfg->freq_num;
+    if (cfg->bin_count > 0) {                                   // validate() has checked the range
+        h->bin0 = cfg->bin_first;
+        h->B = cfg->bin_count;
+        const std::vector<int> bb(h->bin_base.begin() + h->bin0, h->bin_base.begin() + h->bin0 + h->B);
+        const std::vector<int> bs(h->bin_shift.begin() + h->bin0, h->bin_shift.begin() + h->bin0 + h->B);
+        h->bin_base = bb;
+        h->bin_shift = bs;
+    }
     const size_t N = (size_t)h->N;
     const size_t nb = h->base_freq.size();
 
@@ -831,6 +938,20 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     CUC(cudaMemcpyAsync(h->d_bin_shift, h->bin_shift.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaMemcpyAsync(h->d_prn, cfg->prn, h->P * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaMemcpyAsync(h->d_base_freq, h->base_freq.data(), nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        // K1 v2 (comb rows + cp.async staging) whenever its shared memory fits; otherwise the v1 gather kernel
+        const int bps = h->cfg.data_type * h->cfg.data_precision;
+        const int pitch = ((N / 16) * bps + 15) / 16 * 16;
+        if (ops->smem_wipe2(pitch, h->M) <= (size_t)227 * 1024) {
+            std::vector<double> bw(nb);
+            for (size_t i = 0; i < nb; ++i) bw[i] = h->base_freq[i] / h->cfg.fs_hz;
+            CUC(cudaMalloc(&h->d_base_w, nb * sizeof(double)));
+            CUC(cudaMemcpy(h->d_base_w, bw.data(), nb * sizeof(double), cudaMemcpyHostToDevice));
+            h->comb_pitch = pitch;
+            CUC(cudaMalloc(&h->d_comb, (size_t)h->K * h->M * 16 * pitch));
+            CUC(cudaMemset(h->d_comb, 0, (size_t)h->K * h->M * 16 * pitch));
+        }
+    }
 
     // code tables -> HBM, then K0 fills the conj-spectrum cache
     {
@@ -858,9 +979,11 @@ extern "C" int gnssacq_debug_timeline(unsigned long long* out /*[16*16*32]*/) {
     return cudaMemcpy(out, g_timeline, 16 * 16 * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -4;
 }
 #endif
-static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = nullptr) {
+static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = nullptr, bool xchg = false) {
     cudaStream_t s = h->stream;
     h->launches = 0;
+    auto& xc = h->xc;
+    if (xchg && !h->d_comb) return fail(h, GNSSACQ_ERR_STATE, "the multi-GPU exchange needs the comb-row K1 (shared memory too small for this shape)");
     CU(cudaEventRecord(h->ev[1], s));
     const double* means = nullptr;
     if (h->cfg.data_precision == 2) {
@@ -872,19 +995,42 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
         h->launches += 2;
         means = h->d_means;
     }
-    WipeArgs wa;
-    wa.raw = d_if;
-    wa.data_type = h->cfg.data_type;
-    wa.precision = h->cfg.data_precision;
-    wa.coh_ms = h->M;
-    wa.K = h->K;
-    wa.block_bytes = (size_t)h->N * h->M * h->cfg.data_type * h->cfg.data_precision;
-    wa.base_freq_hz = h->d_base_freq;
-    wa.fs_hz = h->cfg.fs_hz;
-    wa.means = means;
-    wa.x = h->d_x;
-    CU(h->ops->launch_wipe(wa, (int)h->base_freq.size() * h->K, s));
-    h->launches += 1;
+    if (h->d_comb) {
+        const int bps = h->cfg.data_type * h->cfg.data_precision;
+        const int rows = h->N / 16, tiles = (rows + kCombTM - 1) / kCombTM;
+        if (xchg) CU(cudaEventRecord(xc.ev_a, s));
+        comb_kernel<<<h->K * h->M * tiles, 256, (size_t)kCombTM * (4 * bps + 1) * 4, s>>>(
+            (const unsigned char*)d_if, h->d_comb, rows, bps, h->comb_pitch, tiles,
+            (xchg && xc.is_root) ? xc.flags : nullptr, (xchg && !xc.is_root) ? xc.flags : nullptr, xc.epoch,
+            xchg ? xc.flags + 63 : nullptr);
+        CU(cudaGetLastError());
+        if (xchg) CU(cudaEventRecord(xc.ev_b, s));
+        Wipe2Args w2;
+        w2.comb = h->d_comb;
+        w2.pitch = h->comb_pitch;
+        w2.bps = bps;
+        w2.coh_ms = h->M;
+        w2.K = h->K;
+        w2.base_w = h->d_base_w;
+        w2.means = means;
+        w2.x = h->d_x;
+        CU(h->ops->launch_wipe2(w2, (int)h->base_freq.size() * h->K, s));
+        h->launches += 2;
+    } else {
+        WipeArgs wa;
+        wa.raw = d_if;
+        wa.data_type = h->cfg.data_type;
+        wa.precision = h->cfg.data_precision;
+        wa.coh_ms = h->M;
+        wa.K = h->K;
+        wa.block_bytes = (size_t)h->N * h->M * h->cfg.data_type * h->cfg.data_precision;
+        wa.base_freq_hz = h->d_base_freq;
+        wa.fs_hz = h->cfg.fs_hz;
+        wa.means = means;
+        wa.x = h->d_x;
+        CU(h->ops->launch_wipe(wa, (int)h->base_freq.size() * h->K, s));
+        h->launches += 1;
+    }
     CU(cudaEventRecord(h->ev[2], s));
     SearchArgs sa;
     sa.cc = h->d_cc;
@@ -893,7 +1039,8 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.bin_shift = h->d_bin_shift;
     sa.P = h->P; sa.B = h->B; sa.K = h->K;
     sa.w = h->w;
-    sa.cand = h->d_cand;
+    sa.cand = xchg ? xc.cand_all + (size_t)xc.sh.prn_first * xc.sh.freq_num_total + xc.sh.bin_first : h->d_cand;
+    sa.cand_stride = xchg ? xc.sh.freq_num_total : h->B;
     sa.surface = h->d_surface;
     sa.scratch = h->d_scratch;
     sa.group_ctr = h->d_group_ctr;
@@ -918,9 +1065,20 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     }
     h->launches += 1;
     CU(cudaEventRecord(h->ev[3], s));
+    if (xchg) {
+        // candidates went straight into the root's table; a non-root shard now raises its "done" flag there,
+        // the root runs K4 over the full table in gnssacq_xchg_finish
+        if (!xc.is_root) {
+            xchg_done_kernel<<<1, 1, 0, s>>>(xc.flags + 1 + xc.sh.rank, xc.epoch);
+            CU(cudaGetLastError());
+            h->launches += 1;
+        }
+        CU(cudaEventRecord(h->ev[4], s));
+        return GNSSACQ_OK;
+    }
     finalize_kernel<<<(h->P + 63) / 64, 64, 0, s>>>(h->d_cand, h->P, h->B, h->N, h->w, h->cfg.freq_min_hz,
                                                     h->cfg.freq_step_hz, h->cfg.snr_threshold_db, h->d_prn,
-                                                    d_out ? d_out : h->d_res);
+                                                    d_out ? d_out : h->d_res, h->B, h->bin0);
     CU(cudaGetLastError());
     h->d_last_rows = d_out ? d_out : h->d_res;
     h->launches += 1;
@@ -964,6 +1122,198 @@ int gnssacq_fetch_results(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats*
         cudaEventElapsedTime(&st->finalize_ms, h->ev[3], h->ev[4]);
         cudaEventElapsedTime(&st->d2h_ms, h->ev[4], h->ev[5]);
         cudaEventElapsedTime(&st->total_ms, h->ev[0], h->ev[5]);
+        st->kernel_launches = h->launches;
+        st->n_bases = (int)h->base_freq.size();
+        st->cluster_ctas = h->ops->R;
+        st->threads = h->ops->T;
+        st->exchange = h->coop_groups > 0 ? 3 : (h->l2x_clusters > 0 ? 2 : 1);
+        st->resident_clusters = h->coop_groups > 0 ? h->coop_groups : h->l2x_clusters;
+        st->work_split = h->d_partial ? 2 : 1;
+    }
+    return GNSSACQ_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU exchange through peer memory
+int gnssacq_shard_plan(const gnssacq_config* full, int32_t rank, int32_t world, gnssacq_config* mine, gnssacq_shard* sh) {
+    std::string why;
+    if (!full || !mine || !sh || world < 1 || world > 62 || rank < 0 || rank >= world) return GNSSACQ_ERR_INVALID_ARG;
+    if (int rc = validate(full, why)) return fail(nullptr, rc, why);
+    if (full->bin_count != 0) return fail(nullptr, GNSSACQ_ERR_INVALID_ARG, "shard_plan wants the full grid (bin_count = 0)");
+    std::memset(sh, 0, sizeof *sh);
+    sh->rank = rank;
+    sh->world = world;
+    sh->n_prn_total = full->n_prn;
+    for (int i = 0; i < full->n_prn; ++i) sh->prn_total[i] = full->prn[i];
+    sh->freq_num_total = full->freq_num;
+    if (full->n_prn >= world) {            // whole PRNs per shard: the per-PRN work never leaves a GPU
+        sh->prn_first = (int32_t)((long long)rank * full->n_prn / world);
+        sh->prn_count = (int32_t)((long long)(rank + 1) * full->n_prn / world) - sh->prn_first;
+        sh->bin_first = 0;
+        sh->bin_count = full->freq_num;
+    } else {                               // fewer PRNs than GPUs: every shard takes all PRNs and a range of bins
+        sh->prn_first = 0;
+        sh->prn_count = full->n_prn;
+        const int q = full->freq_num / world, rem = full->freq_num % world;   // the first `rem` shards take one bin more,
+        sh->bin_first = rank * q + (rank < rem ? rank : rem);                  // so the root always owns rows
+        sh->bin_count = q + (rank < rem ? 1 : 0);
+    }
+    *mine = *full;
+    mine->n_prn = sh->prn_count;
+    for (int i = 0; i < GNSSACQ_MAX_PRN; ++i) mine->prn[i] = i < sh->prn_count ? full->prn[sh->prn_first + i] : 0;
+    mine->bin_first = sh->bin_first;
+    mine->bin_count = sh->bin_count;       // (== freq_num in the PRN-major case: the whole grid)
+    return GNSSACQ_OK;                     // bin_count == 0 (more shards than bins): that shard has no rows and no handle
+}
+
+static int xchg_common(gnssacq_handle* h, const gnssacq_shard* sh) {
+    if (!h || !sh) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (h->xc.on) return fail(h, GNSSACQ_ERR_STATE, "exchange already set up on this handle");
+    if (sh->prn_count != h->P || sh->bin_count != h->B || sh->bin_first != h->bin0 || sh->freq_num_total != h->B_full)
+        return fail(h, GNSSACQ_ERR_INVALID_ARG, "shard does not describe this handle (use gnssacq_shard_plan's config)");
+    if (!h->d_comb) return fail(h, GNSSACQ_ERR_STATE, "the multi-GPU exchange needs the comb-row K1");
+    CU(cudaSetDevice(h->device));
+    h->xc.sh = *sh;
+    for (cudaEvent_t* e : {&h->xc.ev_a, &h->xc.ev_b, &h->xc.ev_c, &h->xc.ev_d}) CU(cudaEventCreate(e));
+    return GNSSACQ_OK;
+}
+static size_t xchg_if_span(const gnssacq_handle* h) { return (h->if_bytes + 255) / 256 * 256; }
+static size_t xchg_cand_span(const gnssacq_shard* sh) {
+    return ((size_t)sh->n_prn_total * sh->freq_num_total * sizeof(Candidate) + 255) / 256 * 256;
+}
+static void xchg_map(gnssacq_handle* h, unsigned char* block) {
+    h->xc.block = block;
+    h->xc.if_buf = block;
+    h->xc.cand_all = reinterpret_cast<Candidate*>(block + xchg_if_span(h));
+    h->xc.flags = reinterpret_cast<unsigned*>(block + xchg_if_span(h) + xchg_cand_span(&h->xc.sh));
+    h->xc.on = true;
+}
+
+int gnssacq_xchg_root(gnssacq_handle* h, const gnssacq_shard* sh, void* ipc_out) {
+    if (int rc = xchg_common(h, sh)) return rc;
+    if (sh->rank != 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "the root is shard 0");
+    unsigned char* block = nullptr;
+    const size_t bytes = xchg_if_span(h) + xchg_cand_span(sh) + 64 * sizeof(unsigned);
+    CU(cudaMalloc(&block, bytes));
+    CU(cudaMemset(block, 0, bytes));
+    h->xc.is_root = true;
+    xchg_map(h, block);
+    CU(cudaMalloc(&h->xc.d_prn_all, sh->n_prn_total * sizeof(int)));
+    CU(cudaMemcpy(h->xc.d_prn_all, sh->prn_total, sh->n_prn_total * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->xc.d_res_all, sh->n_prn_total * sizeof(gnssacq_result)));
+    CU(cudaMallocHost(&h->xc.h_res_all, sh->n_prn_total * sizeof(gnssacq_result)));
+    if (ipc_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) <= GNSSACQ_IPC_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t ih;
+        CU(cudaIpcGetMemHandle(&ih, block));
+        std::memset(ipc_out, 0, GNSSACQ_IPC_BYTES);
+        std::memcpy(ipc_out, &ih, sizeof ih);
+    }
+    return GNSSACQ_OK;
+}
+
+int gnssacq_xchg_attach(gnssacq_handle* h, const gnssacq_shard* sh, const void* root_ipc) {
+    if (!root_ipc) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
+    if (int rc = xchg_common(h, sh)) return rc;
+    if (sh->rank == 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "shard 0 is the root (gnssacq_xchg_root)");
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, root_ipc, sizeof ih);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));      // the root's block, reachable over NVLink
+    h->xc.ipc_opened = true;
+    xchg_map(h, static_cast<unsigned char*>(p));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_xchg_attach_local(gnssacq_handle* h, const gnssacq_shard* sh, gnssacq_handle* root) {
+    if (!root || !root->xc.on || !root->xc.is_root) return fail(h, GNSSACQ_ERR_INVALID_ARG, "root has no exchange block");
+    if (int rc = xchg_common(h, sh)) return rc;
+    if (sh->rank == 0) return fail(h, GNSSACQ_ERR_INVALID_ARG, "shard 0 is the root (gnssacq_xchg_root)");
+    if (h->device != root->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, h->device, root->device));
+        if (!can) return fail(h, GNSSACQ_ERR_CUDA, "no peer access to the root's GPU");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+    }
+    xchg_map(h, root->xc.block);
+    return GNSSACQ_OK;
+}
+
+void* gnssacq_xchg_if_buffer(gnssacq_handle* h) { return (h && h->xc.on && h->xc.is_root) ? h->xc.if_buf : nullptr; }
+
+int gnssacq_xchg_enqueue(gnssacq_handle* h, const void* host_if, size_t nbytes) {
+    if (!h || !h->xc.on) return fail(h, GNSSACQ_ERR_STATE, "no exchange set up on this handle");
+    if (host_if && !h->xc.is_root) return fail(h, GNSSACQ_ERR_INVALID_ARG, "only the root takes the IF block");
+    if (host_if && nbytes < h->if_bytes) return fail(h, GNSSACQ_ERR_SHORT_BUFFER, "IF block shorter than noncoh_blocks*coh_ms ms");
+    CU(cudaSetDevice(h->device));
+    ++h->xc.epoch;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    h->have_h2d = false;
+    if (host_if) {
+        // page-locked caller memory goes to HBM as it is (the caller keeps it unchanged until gnssacq_xchg_fetch);
+        // pageable memory is staged through the library's pinned buffer first (free again on return)
+        cudaPointerAttributes pa{};
+        const bool pinned = cudaPointerGetAttributes(&pa, host_if) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) std::memcpy(h->h_if, host_if, h->if_bytes);
+        CU(cudaMemcpyAsync(h->xc.if_buf, pinned ? host_if : h->h_if, h->if_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->have_h2d = true;
+    }
+    return enqueue(h, h->xc.if_buf, nullptr, true);       // non-root: a peer pointer -- K1a pulls it over NVLink
+}
+
+int gnssacq_xchg_finish(gnssacq_handle* h) {
+    if (!h || !h->xc.on || !h->xc.is_root) return fail(h, GNSSACQ_ERR_STATE, "not the root of an exchange");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    auto& xc = h->xc;
+    CU(cudaEventRecord(xc.ev_c, s));
+    if (xc.sh.world > 1) {
+        xchg_wait_kernel<<<1, 64, 0, s>>>(xc.flags + 1, xc.sh.world, xc.sh.n_prn_total, xc.sh.freq_num_total, xc.epoch, xc.flags + 63);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
+    CU(cudaEventRecord(xc.ev_d, s));
+    finalize_kernel<<<(xc.sh.n_prn_total + 63) / 64, 64, 0, s>>>(xc.cand_all, xc.sh.n_prn_total, xc.sh.freq_num_total, h->N, h->w,
+                                                               h->cfg.freq_min_hz, h->cfg.freq_step_hz, h->cfg.snr_threshold_db,
+                                                               xc.d_prn_all, xc.d_res_all, xc.sh.freq_num_total, 0);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    CU(cudaEventRecord(h->ev[4], s));
+    return GNSSACQ_OK;
+}
+
+int gnssacq_xchg_fetch(gnssacq_handle* h, gnssacq_result* out, gnssacq_stats* st) {
+    if (!h || !h->xc.on) return fail(h, GNSSACQ_ERR_STATE, "no exchange set up on this handle");
+    if (out && !h->xc.is_root) return fail(h, GNSSACQ_ERR_INVALID_ARG, "rows are on the root");
+    CU(cudaSetDevice(h->device));
+    auto& xc = h->xc;
+    const int n = xc.sh.n_prn_total;
+    unsigned timed_out = 0;
+    if (xc.is_root && out) CU(cudaMemcpyAsync(xc.h_res_all, xc.d_res_all, n * sizeof(gnssacq_result), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (xc.is_root) {
+        CU(cudaMemcpy(&timed_out, xc.flags + 63, sizeof timed_out, cudaMemcpyDeviceToHost));
+        if (timed_out) return fail(h, GNSSACQ_ERR_STATE, "a shard of the exchange did not answer within the time-out");
+        if (out) std::memcpy(out, xc.h_res_all, n * sizeof(gnssacq_result));
+    }
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        if (h->have_h2d) cudaEventElapsedTime(&st->h2d_ms, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&st->wipeoff_fft_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&st->search_ms, h->ev[2], h->ev[3]);
+        if (xc.is_root) {
+            // (before gnssacq_xchg_finish these events are unrecorded: the queries fail and leave zeros)
+            if (cudaEventElapsedTime(&st->gather_wait_ms, xc.ev_c, xc.ev_d) != cudaSuccess) st->gather_wait_ms = 0.f;
+            if (cudaEventElapsedTime(&st->finalize_ms, xc.ev_d, h->ev[4]) != cudaSuccess) st->finalize_ms = 0.f;
+            cudaEventElapsedTime(&st->d2h_ms, h->ev[4], h->ev[5]);
+        } else {
+            cudaEventElapsedTime(&st->if_pull_ms, xc.ev_a, xc.ev_b);
+        }
+        cudaEventElapsedTime(&st->total_ms, h->ev[0], h->ev[5]);
+        cudaGetLastError();                    // a failed timing query must not surface at somebody's next launch check
         st->kernel_launches = h->launches;
         st->n_bases = (int)h->base_freq.size();
         st->cluster_ctas = h->ops->R;

@@ -42,6 +42,7 @@ class Config(C.Structure):
         ("snr_threshold_db", C.c_double),
         ("device", C.c_int32), ("cluster_ctas", C.c_int32), ("threads", C.c_int32),
         ("keep_surface", C.c_int32), ("exchange", C.c_int32), ("work_split", C.c_int32),
+        ("bin_first", C.c_int32), ("bin_count", C.c_int32),
     ]
 
 
@@ -85,11 +86,20 @@ class Stats(C.Structure):
         ("finalize_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
         ("kernel_launches", C.c_int32), ("n_bases", C.c_int32), ("cluster_ctas", C.c_int32),
         ("threads", C.c_int32), ("exchange", C.c_int32), ("resident_clusters", C.c_int32),
-        ("work_split", C.c_int32),
+        ("work_split", C.c_int32), ("if_pull_ms", C.c_float), ("gather_wait_ms", C.c_float),
     ]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Shard(C.Structure):
+    """gnssacq_shard: one handle's place in a multi-GPU acquisition (gnssacq_shard_plan)."""
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32), ("n_prn_total", C.c_int32),
+        ("prn_total", C.c_int32 * GNSSACQ_MAX_PRN), ("freq_num_total", C.c_int32),
+        ("prn_first", C.c_int32), ("prn_count", C.c_int32), ("bin_first", C.c_int32), ("bin_count", C.c_int32),
+    ]
 
 
 EXPORTS = (
@@ -99,6 +109,8 @@ EXPORTS = (
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
     "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_sweep_file", "gnssacq_track_load", "gnssacq_correlate",
     "gnssacq_loop_params_default", "gnssacq_track",
+    "gnssacq_shard_plan", "gnssacq_xchg_root", "gnssacq_xchg_attach", "gnssacq_xchg_attach_local",
+    "gnssacq_xchg_if_buffer", "gnssacq_xchg_enqueue", "gnssacq_xchg_finish", "gnssacq_xchg_fetch",
 )
 
 
@@ -135,6 +147,15 @@ def _load() -> C.CDLL:
     lib.gnssacq_correlate.argtypes = [vp, C.c_int32, C.POINTER(Channel), C.c_int32, vp, vp, vp]
     lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_sweep_file.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(Result), C.POINTER(Stats)]
+    lib.gnssacq_shard_plan.argtypes = [C.POINTER(Config), C.c_int32, C.c_int32, C.POINTER(Config), C.POINTER(Shard)]
+    lib.gnssacq_xchg_root.argtypes = [vp, C.POINTER(Shard), vp]
+    lib.gnssacq_xchg_attach.argtypes = [vp, C.POINTER(Shard), vp]
+    lib.gnssacq_xchg_attach_local.argtypes = [vp, C.POINTER(Shard), vp]
+    lib.gnssacq_xchg_if_buffer.argtypes = [vp]
+    lib.gnssacq_xchg_if_buffer.restype = vp
+    lib.gnssacq_xchg_enqueue.argtypes = [vp, vp, C.c_size_t]
+    lib.gnssacq_xchg_finish.argtypes = [vp]
+    lib.gnssacq_xchg_fetch.argtypes = [vp, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_fp32_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     return lib
 
@@ -156,7 +177,8 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
                 data_type=2, data_precision=1, freq_min_hz=-10000.0, freq_step_hz=500.0,
                 freq_num: Optional[int] = None, noncoh_blocks=20, coh_ms=1,
                 prns: Sequence[int] = tuple(range(1, 33)), snr_threshold_db=12.0, device=-1,
-                cluster_ctas=0, threads=0, keep_surface=False, exchange=0, work_split=0) -> Config:
+                cluster_ctas=0, threads=0, keep_surface=False, exchange=0, work_split=0,
+                bin_first=0, bin_count=0) -> Config:
     cfg = default_config()
     cfg.fs_hz, cfg.if_hz, cfg.code_hz = fs_hz, if_hz, code_hz
     cfg.samples_per_ms = int(samples_per_ms if samples_per_ms else np.ceil(fs_hz * 1e-3))
@@ -175,7 +197,21 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
     cfg.keep_surface = int(bool(keep_surface))
     cfg.exchange = int(exchange)
     cfg.work_split = int(work_split)
+    cfg.bin_first, cfg.bin_count = int(bin_first), int(bin_count)
     return cfg
+
+
+def shard_plan(cfg: Config, rank: int, world: int):
+    """gnssacq_shard_plan: (this shard's Config, its Shard).  Whole PRNs per shard when n_prn >= world, else all
+    PRNs and a range of Doppler bins; a shard with ``bin_count == 0`` has no rows (more shards than bins)."""
+    mine, sh = Config(), Shard()
+    rc = lib.gnssacq_shard_plan(C.byref(cfg), rank, world, C.byref(mine), C.byref(sh))
+    if rc:
+        raise GnssAcqError(rc, (lib.gnssacq_last_error(None) or b"").decode())
+    return mine, sh
+
+
+IPC_BYTES = 64
 
 
 def ca_code(prn: int) -> np.ndarray:
@@ -296,6 +332,46 @@ class Searcher:
         self._check(lib.gnssacq_fetch_results(self._h, None, C.byref(st)))
         self.last_stats = st
         return st
+
+    # ---- multi-GPU exchange through peer memory (include/gnssacq.h: gnssacq_xchg_*) ----
+    def xchg_root(self, shard: "Shard") -> bytes:
+        """Make this handle the root of a sharded acquisition; returns the IPC handle other processes attach to."""
+        buf = C.create_string_buffer(IPC_BYTES)
+        self._check(lib.gnssacq_xchg_root(self._h, C.byref(shard), buf))
+        self.shard = shard
+        return buf.raw
+
+    def xchg_attach(self, shard: "Shard", root_ipc: bytes) -> None:
+        self._check(lib.gnssacq_xchg_attach(self._h, C.byref(shard), C.c_char_p(root_ipc)))
+        self.shard = shard
+
+    def xchg_attach_local(self, shard: "Shard", root: "Searcher") -> None:
+        self._check(lib.gnssacq_xchg_attach_local(self._h, C.byref(shard), root._h))
+        self.shard = shard
+
+    def xchg_if_buffer(self) -> int:
+        return int(lib.gnssacq_xchg_if_buffer(self._h) or 0)
+
+    def xchg_enqueue(self, host_if=None) -> None:
+        if host_if is None:
+            self._check(lib.gnssacq_xchg_enqueue(self._h, None, 0))
+        else:
+            buf = np.ascontiguousarray(np.frombuffer(host_if, dtype=np.uint8) if not isinstance(host_if, np.ndarray) else host_if)
+            self._check(lib.gnssacq_xchg_enqueue(self._h, buf.ctypes.data, buf.nbytes))
+
+    def xchg_finish(self) -> None:
+        self._check(lib.gnssacq_xchg_finish(self._h))
+
+    def xchg_fetch(self, rows: bool = True) -> List[Result]:
+        st = Stats()
+        if rows:
+            out = (Result * self.shard.n_prn_total)()
+            self._check(lib.gnssacq_xchg_fetch(self._h, out, C.byref(st)))
+            self.last_stats = st
+            return list(out)
+        self._check(lib.gnssacq_xchg_fetch(self._h, None, C.byref(st)))
+        self.last_stats = st
+        return []
 
     def track_load(self, if_bytes) -> None:
         """Keep a segment of the recording resident in HBM for `correlate`."""

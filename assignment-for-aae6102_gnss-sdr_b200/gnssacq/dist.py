@@ -33,9 +33,151 @@ def shard_sizes(n_prn: int, world: int) -> List[int]:
     return [(r + 1) * n_prn // world - r * n_prn // world for r in range(world)]
 
 
+def merge_candidates(cands, n_samples: int, w: int, fmin: float, fstep: float, thr: float = 12.0):
+    """Host statement of what K4 (finalize_kernel) does with one PRN's row candidates, whichever GPU produced
+    them (bin-split shards): ``cands[b] = (peak, lag, sum_all, sum_win)`` for every Doppler bin b of
+    the FULL grid.  Winner = the maximum peak; among equal peaks the LOWEST bin (acquisition.m:62) and the lowest
+    code phase (:63); the noise floor comes from the winning bin's own tuple with the reference's clipped index set
+    (:66-68).  Returns (code_phase, doppler_bin, doppler_hz, peak, noise_meansq, snr_db, acquired).  Used by the
+    CPU tests of the multi-GPU merge; the product runs the same rule on the root GPU."""
+    import math
+    g = max(c[0] for c in cands)
+    tied = [b for b, c in enumerate(cands) if c[0] == g]
+    fbin = tied[0]
+    cp = min(cands[b][1] for b in tied)
+    cp1 = cp + 1
+    cnt = max(cp1 - w, 0) + max(n_samples - cp1 - w + 1, 0)
+    noise = (cands[fbin][2] - cands[fbin][3]) / cnt if cnt else float("nan")
+    snr = 10.0 * math.log10(g * g / noise) if noise > 0 else float("nan")
+    return cp, fbin, fmin + fstep * fbin, g, noise, snr, bool(snr >= thr)
+
+
 def rows_from_bytes(buf: bytes) -> List[api.Result]:
     n = len(buf) // ROW_BYTES
     return list((api.Result * n).from_buffer_copy(buf[: n * ROW_BYTES]))
+
+
+class PeerShard:
+    """One rank's share of ONE acquisition, exchanged through peer memory instead of NCCL (gnssacq_xchg_*):
+    rank 0 holds the IF buffer and the candidate table of the full grid; the other ranks' K1a pulls the IF
+    block out of rank 0's HBM over NVLink, their K2 stores its row candidates straight into rank 0's table,
+    and rank 0 runs K4 over the full table -- so the rows are byte-identical for every world size, also when
+    there are fewer PRNs than GPUs (then the Doppler bins are split).  `torch.distributed` is used once, to
+    hand rank 0's CUDA IPC handle to the other processes.  No CPU fallback."""
+
+    def __init__(self, cfg_full: api.Config, rank: int, world: int, device: int, dist=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        torch.cuda.set_device(device)
+        full = api.Config.from_buffer_copy(bytes(cfg_full))
+        full.device = device
+        mine, self.shard = api.shard_plan(full, rank, world)
+        self.n_prn_total = self.shard.n_prn_total
+        self.rows_local = self.shard.prn_count * self.shard.bin_count
+        self.searcher = api.Searcher(mine) if self.rows_local > 0 else None
+        self.if_bytes = int(api.lib.gnssacq_if_bytes(C.byref(full)))
+        ipc = [None]
+        if rank == 0:
+            if self.searcher is None:
+                raise ValueError("rank 0 must own rows")
+            ipc[0] = self.searcher.xchg_root(self.shard)
+        if world > 1:
+            dist.broadcast_object_list(ipc, src=0)
+        if rank != 0 and self.searcher:
+            self.searcher.xchg_attach(self.shard, ipc[0])
+        self.d_if_ptr = self.searcher.xchg_if_buffer() if rank == 0 else 0
+
+    def bind_stream(self) -> None:
+        if self.searcher:
+            self.searcher.set_stream(self.torch.cuda.current_stream().cuda_stream)
+
+    def upload(self, h_if) -> None:
+        """rank 0: put an IF block into the exchange buffer (for device-resident timing loops)."""
+        if self.rank == 0:
+            t = self.torch.frombuffer(bytearray(h_if), dtype=self.torch.uint8) if not hasattr(h_if, "data_ptr") else h_if
+            self._copy_into_if(t)
+
+    def _copy_into_if(self, t) -> None:
+        torch = self.torch
+        # wrap the exchange block's IF buffer as a tensor (no ownership) and copy with torch's own stream ordering
+        arr = _DevArray(self.d_if_ptr, self.if_bytes)
+        dst = torch.as_tensor(arr, device="cuda")
+        dst.copy_(t[: self.if_bytes], non_blocking=True)
+
+    def enqueue(self, host_if=None) -> None:
+        """One step on torch's current stream.  rank 0: `host_if` (bytes-like, pageable is fine: the library
+        stages it) or None when the block is already in the exchange buffer."""
+        self.bind_stream()
+        if self.searcher is None:
+            return
+        self.searcher.xchg_enqueue(host_if if self.rank == 0 else None)
+        if self.rank == 0:
+            self.searcher.xchg_finish()
+
+    def fetch(self) -> List[api.Result]:
+        """rank 0: host sync + all rows (original PRN order); other ranks: host sync, []."""
+        if self.searcher is None:
+            return []
+        return self.searcher.xchg_fetch(rows=(self.rank == 0))
+
+    def close(self) -> None:
+        if self.searcher:
+            self.searcher.close()
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ view of raw device memory (uint8)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class LocalMultiGpu:
+    """The same exchange inside ONE process: shard r on devices[r] (what a MATLAB host can drive without
+    torchrun).  If several shards share a device (tests on a one-GPU box), the steps are serialised with host
+    syncs, because kernels of different shards that wait for one another must not share a GPU."""
+
+    def __init__(self, cfg_full: api.Config, devices: Sequence[int]):
+        self.world = len(devices)
+        self.serial = len(set(devices)) < len(devices)
+        self.searchers: List[api.Searcher] = []
+        self.shards = []
+        for r, dev in enumerate(devices):
+            full = api.Config.from_buffer_copy(bytes(cfg_full))
+            full.device = dev
+            mine, sh = api.shard_plan(full, r, self.world)
+            self.shards.append(sh)
+            self.searchers.append(api.Searcher(mine) if sh.prn_count * sh.bin_count > 0 else None)
+        root = self.searchers[0]
+        root.xchg_root(self.shards[0])
+        for s, sh in zip(self.searchers[1:], self.shards[1:]):
+            if s:
+                s.xchg_attach_local(sh, root)
+
+    def search(self, if_bytes) -> List[api.Result]:
+        root = self.searchers[0]
+        root.xchg_enqueue(if_bytes)
+        if self.serial:
+            root.xchg_fetch(rows=False)
+        for s in self.searchers[1:]:
+            if s:
+                s.xchg_enqueue(None)
+                if self.serial:
+                    s.xchg_fetch(rows=False)
+        root.xchg_finish()
+        return root.xchg_fetch()
+
+    def close(self) -> None:
+        for s in self.searchers[1:] + self.searchers[:1]:
+            if s:
+                s.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class CudaShard:

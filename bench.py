@@ -68,6 +68,19 @@ def synth_bytes(cfg) -> bytes:
     return rec.read(0, cfg["k"] * cfg["m"])
 
 
+def sparse_recording(cfg, raws, n_epochs, path):
+    """A recording file for the config-4 sweep: `n_epochs` epochs of `epoch_ms`, the first K*M ms of each holding
+    one of the synthetic windows (cycled); the rest of each epoch is a hole (never read by the sweep).  90 s at
+    58 MHz int8 I/Q is 10.44 GB of file offsets but only n_epochs x 2.32 MB of data."""
+    ms_bytes = cfg["n"] * 2
+    with open(path, "wb") as f:
+        for j in range(n_epochs):
+            f.seek(j * cfg["epoch_ms"] * ms_bytes)
+            f.write(raws[j % len(raws)])
+        f.truncate(max(f.tell(), (n_epochs - 1) * cfg["epoch_ms"] * ms_bytes + len(raws[0])))
+    return path
+
+
 def synth_windows(cfg) -> list:
     """The first few windows of a re-acquisition sweep (config 4): window j starts at ms epoch_ms * j."""
     from gnssacq.synth import opensky_recording, urban_recording
@@ -277,7 +290,7 @@ def run_gpu(args, cfg):
     import torch.distributed as dist
     import gnssacq
     from gnssacq import api
-    from gnssacq.dist import CudaShard, ROW_BYTES
+    from gnssacq.dist import CudaShard, PeerShard, ROW_BYTES
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -297,12 +310,34 @@ def run_gpu(args, cfg):
     sweep = "sweep_windows" in cfg
     raws = synth_windows(cfg) if sweep else [synth_bytes(cfg)]
     raw = raws[0]
-    shard = CudaShard(factory, PRNS, rank, world, local)
-    shard.bind_stream()
     h_ifs = [torch.frombuffer(bytearray(r), dtype=torch.uint8).pin_memory() for r in raws]
     d_ifs = [h.cuda() for h in h_ifs] if sweep else []
     h_if = h_ifs[0]
-    shard.d_if.copy_(h_if)
+    peer = args.xchg == "peer"
+    if peer:
+        # exchange through peer memory (gnssacq_xchg_*): no NCCL inside a step.  Same call shape as CudaShard below.
+        ps = PeerShard(factory(PRNS, local), rank, world, local, dist if world > 1 else None)
+
+        class _Shard:
+            searcher, n_local, max_rows = ps.searcher, ps.shard.prn_count, (len(PRNS) + world - 1) // world
+
+            @staticmethod
+            def enqueue(_d, h_if=None):
+                ps.enqueue(h_if.numpy() if (h_if is not None and rank == 0) else None)
+
+            fetch = staticmethod(ps.fetch)
+            close = staticmethod(ps.close)
+
+            @staticmethod
+            def load(t):
+                ps.upload(t)
+        shard = _Shard
+        shard.load(h_if)
+    else:
+        shard = CudaShard(factory, PRNS, rank, world, local)
+        shard.bind_stream()
+        shard.d_if.copy_(h_if)
+        shard.load = lambda t: shard.d_if.copy_(t)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     d = dist if world > 1 else None
 
@@ -330,7 +365,7 @@ def run_gpu(args, cfg):
                 # leaks into this rank's step through the broadcast inside it
                 dist.all_reduce(sync_t)
             if sweep:
-                shard.d_if.copy_(d_ifs[i % len(d_ifs)])     # this step's window: resident in HBM, outside the timed pair
+                shard.load(d_ifs[i % len(d_ifs)])           # this step's window: resident in HBM, outside the timed pair
             ev0[i].record()
             shard.enqueue(d)
             ev1[i].record()
@@ -343,16 +378,22 @@ def run_gpu(args, cfg):
     total_ms = float(total_ms.item())
 
     # ---- roofline pass: dominant kernel (search_kernel) duration from the library's own events ----
-    k2_ms, k1_ms, launches = [], [], 0
-    scratch = (api.Result * max(shard.n_local, 1))()
+    k2_ms, k1_ms, launches, pull_ms, wait_ms = [], [], 0, [], []
     for i in range(min(args.steps, 20)):
         flush.zero_()
+        if world > 1:
+            dist.all_reduce(sync_t)
         shard.enqueue(d)
         if shard.searcher:
-            st = api.Stats()
-            api.lib.gnssacq_fetch_results(shard.searcher._h, scratch, st)
+            if peer:
+                shard.fetch()
+                st = shard.searcher.last_stats
+            else:
+                st = shard.searcher.fetch_stats()
             k2_ms.append(st.search_ms)
             k1_ms.append(st.wipeoff_fft_ms)
+            pull_ms.append(st.if_pull_ms)
+            wait_ms.append(st.gather_wait_ms)
             launches = st.kernel_launches
     torch.cuda.synchronize()
     variant = (st.cluster_ctas, st.threads) if shard.searcher else (0, 0)
@@ -362,10 +403,19 @@ def run_gpu(args, cfg):
     t0 = time.perf_counter()
     e2e_api = "CudaShard.enqueue(h_if) + fetch: pinned H2D on rank 0, IF exchange, shard search, row exchange, D2H"
     if sweep and world == 1:
-        # the public call for this workload: one gnssacq_sweep over `steps` host windows
-        swept = shard.searcher.sweep([raws[i % len(raws)] for i in range(args.steps)])
+        # the public call for this workload: ONE gnssacq_sweep_file over `steps` epochs of a recording on disk --
+        # the library does acquisition.m:27-34's fseek/fread itself, straight into pinned staging, overlapped
+        import tempfile
+        tmpdir = tempfile.mkdtemp(prefix="gnssacq_rec_")
+        rec = sparse_recording(cfg, raws, args.steps, os.path.join(tmpdir, "Opensky_synth_90s.bin"))
+        barrier()
+        t0 = time.perf_counter()
+        swept = shard.searcher.sweep_file(rec, 0, cfg["epoch_ms"], args.steps)
         rows = swept[-1]
-        e2e_api = "gnssacq_sweep (Searcher.sweep): host windows -> library staging -> H2D -> search -> D2H"
+        os.remove(rec)
+        os.rmdir(tmpdir)
+        e2e_api = (f"gnssacq_sweep_file (Searcher.sweep_file): {args.steps} epochs, one every {cfg['epoch_ms']} ms, read by the library "
+                   "from a recording file (fseek + fread into pinned staging) -> H2D -> K1/K2/K4 -> one D2H of all rows")
     elif world == 1:
         # the call the MEX gateway makes (matlab/gnssacq_mex.c -> gnssacq_search): caller-owned pageable host
         # buffer in, result rows out; staging copy, H2D, kernels, D2H and the host sync are all inside
@@ -385,6 +435,10 @@ def run_gpu(args, cfg):
     e2e_s = float(e2e_s.item())
 
     cells = len(PRNS) * cfg["bins"] * cfg["n"]
+    # per-phase times of the exchange (SURVEY 5 metrics row): slowest non-root IF pull, the root's wait for candidates
+    phase = torch.tensor([max(pull_ms) if pull_ms and rank else 0.0, sum(k2_ms) / max(len(k2_ms), 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(phase, op=dist.ReduceOp.MAX)
     if rank == 0:
         n_local = shard.n_local
         nb = st.n_bases
@@ -416,6 +470,11 @@ def run_gpu(args, cfg):
                                   "resident_clusters": st.resident_clusters,
                                   "work_split": {1: "whole rows", 2: "block-granular tail"}.get(st.work_split)},
                        "sharding": f"PRN-major, {n_local} PRNs on rank 0",
+                       "exchange_between_gpus": ("peer memory (CUDA IPC over NVLink): K1a pulls the IF block from rank 0, K2 stores its "
+                                                 "candidates into rank 0's table, K4 on rank 0; no NCCL call inside a step" if peer else
+                                                 "NCCL broadcast of the IF block + all_gather of the result rows") if world > 1 else "none (one GPU)",
+                       "exchange_phases_ms": {"if_pull_max_over_ranks": float(phase[0].item()), "gather_wait_rank0": (sum(wait_ms) / len(wait_ms)) if wait_ms else 0.0,
+                                              "search_kernel_max_over_ranks": float(phase[1].item())},
                        "latency_ms_32prn": e2e_s / args.steps * 1e3,
                        **({"sweep": f"{len(raws)} distinct windows, one every {cfg['epoch_ms']} ms, cycled; e2e = one gnssacq_sweep call over {args.steps} host windows"
                            if world == 1 else f"{len(raws)} distinct windows cycled, one host window per step"} if sweep else {})},
@@ -453,6 +512,84 @@ def run_gpu(args, cfg):
         dist.destroy_process_group()
 
 
+def run_gpu_epoch_sharded(args, cfg):
+    """BASELINE config 4, the other way to use N GPUs: the EPOCHS of the sweep are dealt out, rank r takes
+    epochs r, r + N, ...; every rank searches all 32 PRNs of its epochs on its own GPU and nothing is exchanged
+    (no collective on the data path).  A step is still one epoch; `steps` epochs in total."""
+    import torch
+    import torch.distributed as dist
+    import gnssacq
+    from gnssacq import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    raws = synth_windows(cfg)
+    mine = list(range(rank, args.steps, world))                       # this rank's epochs
+    s = api.Searcher(gnssacq.make_config(fs_hz=cfg["fs"], if_hz=cfg["if_hz"], samples_per_ms=cfg["n"], freq_min_hz=cfg["fmin"],
+                                         freq_step_hz=cfg["fstep"], freq_num=cfg["bins"], noncoh_blocks=cfg["k"], coh_ms=cfg["m"],
+                                         prns=PRNS, device=local))
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    d_ifs = [torch.frombuffer(bytearray(r), dtype=torch.uint8).cuda() for r in raws]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for i in range(max(args.warmup, 3)):
+        s.enqueue_device(d_ifs[i % len(d_ifs)].data_ptr(), s.if_bytes)
+    s.fetch()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in mine]
+    barrier()
+    with ClockSampler(local) as clk:
+        for (a, b), j in zip(ev, mine):
+            flush.zero_()
+            a.record()
+            s.enqueue_device(d_ifs[j % len(d_ifs)].data_ptr(), s.if_bytes)
+            b.record()
+        barrier()
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    # end to end: this rank's epochs straight from the recording file, one gnssacq_sweep_file call
+    import tempfile
+    tmpdir = tempfile.mkdtemp(prefix="gnssacq_rec_")
+    rec = sparse_recording(cfg, raws, args.steps, os.path.join(tmpdir, f"rec_rank{rank}.bin"))
+    barrier()
+    t0 = time.perf_counter()
+    swept = s.sweep_file(rec, rank * cfg["epoch_ms"], world * cfg["epoch_ms"], len(mine)) if mine else []
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    os.remove(rec)
+    os.rmdir(tmpdir)
+    st = s.last_stats
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    cells = len(PRNS) * cfg["bins"] * cfg["n"]
+    if rank == 0:
+        rows = swept[-1]
+        line = {"metric": METRIC, "value": cells * args.steps / (float(total_ms.item()) * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(total_ms.item()) / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(cfg),
+                "run": {"sharding": f"epoch-sharded: rank r searches epochs r, r+{world}, ... with all 32 PRNs; no exchange between GPUs",
+                        "latency_ms_32prn": st.total_ms / max(len(mine), 1)},
+                "e2e": {"value": cells * args.steps / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": len(raws[0]),
+                        "d2h_bytes_per_step": 32 * 56,
+                        "api": "gnssacq_sweep_file per rank over its epochs of the recording (fseek/fread by the library)"},
+                "gpu_launches": 4 * args.steps, "clocks": clk.summary(),
+                "acquired": [r.prn for r in rows if r.acquired]}
+        if not args.no_parity:
+            line["parity_checked"] = parity_check(cfg, raws[mine[-1] % len(raws)], rows, [3, 8, 22, 30])
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -464,12 +601,18 @@ def main():
     ap.add_argument("--cluster-ctas", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--exchange", type=int, default=0, help="0 auto, 1 DSMEM, 2 L2-resident exchange buffer")
+    ap.add_argument("--xchg", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU exchange: peer memory (gnssacq_xchg_*, default) or the r01 NCCL broadcast + all-gather")
+    ap.add_argument("--sweep-shard", default="grid", choices=["grid", "epochs"],
+                    help="config 4 on N GPUs: shard every acquisition's PRN x Doppler grid (default, BASELINE's wording) or deal out the epochs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.sweep_shard == "epochs" and "sweep_windows" in cfg:
+        run_gpu_epoch_sharded(args, cfg)
     else:
         run_gpu(args, cfg)
 

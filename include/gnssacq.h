@@ -71,6 +71,10 @@ typedef struct gnssacq_config {
                                  costs (noncoh_blocks - 1) planes of samples_per_ms floats per group of HBM).
                                  0 = auto: 2 where it pays -- a handle with few rows (one rank's shard at 8 GPUs,
                                  a single-PRN re-acquisition) --, else 1 */
+    int32_t bin_first;        /* this handle searches Doppler bins [bin_first, bin_first + bin_count) of the grid */
+    int32_t bin_count;        /* (a rank's shard when there are fewer PRNs than GPUs); 0 = all freq_num
+                                 bins.  The forward transforms are planned on the FULL grid, so a sub-range produces
+                                 bit for bit the candidates the full search has for those bins */
 } gnssacq_config;
 
 /* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */
@@ -101,6 +105,9 @@ typedef struct gnssacq_stats {
     int32_t exchange;         /* 1 = DSMEM, 2 = L2 + clusters, 3 = L2 + cooperative groups */
     int32_t resident_clusters;/* persistent clusters / CTA groups of the search kernel (0 for DSMEM) */
     int32_t work_split;       /* schedule actually used: 1 = whole rows, 2 = block-granular tail */
+    float if_pull_ms;         /* multi-GPU exchange: K1a on a non-root shard = wait for the root's IF block + pull it over
+                                 NVLink + re-order (0 on the root / single GPU, where it is part of wipeoff_fft_ms) */
+    float gather_wait_ms;     /* multi-GPU exchange, root: waiting for the other shards' candidates after its own search */
 } gnssacq_stats;
 
 typedef struct gnssacq_handle gnssacq_handle;
@@ -165,6 +172,47 @@ int gnssacq_search_multi(gnssacq_handle* const* hs, int32_t n_handles, const voi
  * the last window. */
 int gnssacq_sweep(gnssacq_handle* h, const void* const* windows, int32_t n_windows, size_t nbytes_each,
                   gnssacq_result* out, gnssacq_stats* stats);
+
+/* ---- one acquisition sharded over several GPUs, exchange through peer memory (no NCCL in the step) -------------
+ * SURVEY 8e.  The (PRN, Doppler bin) rows of ONE acquisition are dealt out to `world` handles, one per GPU
+ * (processes or one process): whole PRNs per shard when n_prn >= world, otherwise every shard takes all PRNs and a
+ * range of bins (gnssacq_shard_plan).  Shard 0 is the root.  Its exchange block -- IF buffer, candidate table of the
+ * FULL grid [n_prn][freq_num], flags -- is mapped into the other shards (CUDA IPC between processes,
+ * peer access inside one process).  One step:
+ *   root   : [H2D of the IF block] -> K1a (publishes "IF ready") -> K1b -> K2 (candidates into its own table)
+ *   others : K1a waits for "IF ready", PULLS the IF block out of the root's HBM over NVLink (16-byte vector loads)
+ *            -> K1b -> K2, which STORES its row candidates straight into the root's table over NVLink -> "done" flag
+ *   root   : waits for every "done" flag -> K4 over the full table (first bin / first code phase over ALL bins,
+ *            acquisition.m:62-68) -> rows.
+ * Because K4 sees exactly the candidates a single-GPU search computes, the rows are byte-identical for any world.
+ * All calls are stream-ordered and return at once, except gnssacq_xchg_fetch.  Every shard must call
+ * gnssacq_xchg_enqueue the same number of times (the flags carry a step counter). */
+typedef struct gnssacq_shard {
+    int32_t rank, world;
+    int32_t n_prn_total;                  /* the whole acquisition */
+    int32_t prn_total[GNSSACQ_MAX_PRN];
+    int32_t freq_num_total;
+    int32_t prn_first, prn_count;         /* this shard's rows: PRNs [prn_first, +prn_count) x bins [bin_first, +bin_count) */
+    int32_t bin_first, bin_count;
+} gnssacq_shard;
+#define GNSSACQ_IPC_BYTES 64
+/* full config + (rank, world) -> this shard's config (`mine`: PRN subset and bin range filled in) and its place */
+int gnssacq_shard_plan(const gnssacq_config* full, int32_t rank, int32_t world, gnssacq_config* mine, gnssacq_shard* shard);
+/* root only: allocate the exchange block; ipc_out (GNSSACQ_IPC_BYTES, may be NULL) receives the handle other
+ * PROCESSES open with gnssacq_xchg_attach */
+int gnssacq_xchg_root(gnssacq_handle* root, const gnssacq_shard* shard, void* ipc_out);
+int gnssacq_xchg_attach(gnssacq_handle* h, const gnssacq_shard* shard, const void* root_ipc);        /* other process */
+int gnssacq_xchg_attach_local(gnssacq_handle* h, const gnssacq_shard* shard, gnssacq_handle* root); /* same process */
+/* device pointer of the root's IF buffer (gnssacq_if_bytes): for callers whose samples are already in HBM */
+void* gnssacq_xchg_if_buffer(gnssacq_handle* root);
+/* one step of this shard.  host_if: root only -- NULL = the IF block is already in the exchange block's buffer,
+ * else it is copied there first: pageable memory through the library's pinned staging buffer (the caller's
+ * buffer is free on return), page-locked memory directly (keep it unchanged until gnssacq_xchg_fetch) */
+int gnssacq_xchg_enqueue(gnssacq_handle* h, const void* host_if, size_t nbytes);
+/* root only: wait for every shard, K4 over the full table (stream-ordered, no host sync) */
+int gnssacq_xchg_finish(gnssacq_handle* root);
+/* root only: host sync + the n_prn_total rows of the last finished step */
+int gnssacq_xchg_fetch(gnssacq_handle* root, gnssacq_result* out, gnssacq_stats* stats /* may be NULL */);
 
 /* The same sweep read straight from a recording file (BASELINE config 4: one acquisition every epoch_ms over a
  * 90 s recording = 900 windows).  Window j = the bytes acquisition.m:27-34 reads with file.skip = skip_ms +

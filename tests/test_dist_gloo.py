@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 import gnssacq
 from gnssacq import api
-from gnssacq.dist import prn_shard, shard_sizes, merge_table, gather_rows_host, ROW_BYTES
+from gnssacq.dist import prn_shard, shard_sizes, merge_table, gather_rows_host, merge_candidates, ROW_BYTES
 from helpers import structs, small_spec, oracle_rows
 from oracle.synth import synth_if
 
@@ -85,3 +85,94 @@ def test_world2_gloo_table_equals_single_process():
     want = [(r.prn, r.code_phase, r.doppler_bin, int(r.acquired), r.peak)
             for r in oracle_rows(raw, file, signal, acq, [1, 3, 7, 22, 30])]
     assert got == want
+
+
+# ---------------------------------------------------------------- bin-split shards (fewer PRNs than GPUs)
+def test_shard_plan_tiles_the_grid():
+    """gnssacq_shard_plan (host only): the shards' (PRN range x bin range) rectangles tile the (PRN, bin) grid
+    exactly once -- whole PRNs when n_prn >= world, all PRNs x a bin range otherwise."""
+    for prns, bins, world in [(list(range(1, 33)), 41, 8), (list(range(1, 33)), 41, 5), ([7], 41, 8), ([3, 9, 30], 2001, 8),
+                              ([3, 9, 30], 41, 2), ([5], 3, 8), (list(range(1, 9)), 41, 8)]:
+        cfg = gnssacq.make_config(prns=prns, freq_num=bins, freq_step_hz=500.0)
+        seen = np.zeros((len(prns), bins), dtype=int)
+        sizes = []
+        for r in range(world):
+            mine, sh = api.shard_plan(cfg, r, world)
+            assert (sh.rank, sh.world, sh.n_prn_total, sh.freq_num_total) == (r, world, len(prns), bins)
+            assert list(mine.prn[: mine.n_prn]) == prns[sh.prn_first: sh.prn_first + sh.prn_count]
+            assert (mine.bin_first, mine.bin_count) == (sh.bin_first, sh.bin_count)
+            seen[sh.prn_first: sh.prn_first + sh.prn_count, sh.bin_first: sh.bin_first + sh.bin_count] += 1
+            sizes.append(sh.prn_count * sh.bin_count)
+            if len(prns) >= world:
+                assert sh.bin_count == bins and sh.prn_count >= 1
+            else:
+                assert sh.prn_count == len(prns)
+        assert (seen == 1).all()
+        if len(prns) >= world or bins >= world:
+            assert max(sizes) - min(sizes) <= max(len(prns), bins)
+    with pytest.raises(gnssacq.GnssAcqError):
+        api.shard_plan(gnssacq.make_config(prns=[1]), 2, 2)
+
+
+def _cand_of_rows(surface, w):
+    """(peak, first lag, sum of squares, windowed sum of squares) of every bin row: what K2/K3 emit per row."""
+    out = []
+    n = surface.shape[1]
+    for row in surface:
+        lag = int(np.argmax(row))
+        lo, hi = max(lag - (w - 1), 0), min(lag + (w - 1), n - 1)
+        out.append((float(row[lag]), lag, float(np.sum(row ** 2)), float(np.sum(row[lo:hi + 1] ** 2))))
+    return out
+
+
+def _bin_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import math
+    import oracle
+    from oracle.acquisition_ref import correlation_surface, samples_from_bytes
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1500.0, freq_step=500.0, freq_num=7)
+    n = int(signal.Sample)
+    raw = torch.frombuffer(bytearray(synth_if(small_spec(fs, if_hz, n), 0, 2)), dtype=torch.uint8).clone() \
+        if rank == 0 else torch.empty(n * 2 * 2, dtype=torch.uint8)
+    dist.broadcast(raw, src=0)
+    cfg = gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=[7], freq_min_hz=-1500.0, freq_step_hz=500.0, freq_num=7, noncoh_blocks=2)
+    mine, sh = api.shard_plan(cfg, rank, world)                       # one PRN, two ranks: bins are split
+    assert sh.prn_count == 1 and sh.bin_count in (3, 4)
+    sub = oracle.AcqParams(freqStep=500.0, freqMin=-1500.0 + 500.0 * sh.bin_first, freqNum=sh.bin_count, datalen=2)
+    surf = correlation_surface(samples_from_bytes(raw.numpy().tobytes(), 2, 1), signal, sub, 7)   # the oracle stands in for this rank's GPU
+    w = int(math.ceil(fs / 1.023e6))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (sh.bin_first, _cand_of_rows(surf, w)))
+    if rank == 0:
+        table = [None] * 7
+        for b0, cands in gathered:
+            table[b0: b0 + len(cands)] = cands
+        q.put(merge_candidates(table, n, w, -1500.0, 500.0))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_bin_split_merge_equals_single_search():
+    """One PRN on two ranks (P < G): every rank searches a range of Doppler bins, the winner tuples are merged with
+    K4's rule (max peak, lowest bin, lowest code phase, noise from the winner's own row) -- same row as the
+    single-process oracle search of the whole grid (acquisition.m:62-68)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bin_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    cp, fbin, dop, peak, noise, snr, acquired = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1500.0, freq_step=500.0, freq_num=7)
+    raw = synth_if(small_spec(fs, if_hz, int(signal.Sample)), 0, 2)
+    ref = oracle_rows(raw, file, signal, acq, [7])[0]
+    assert (cp, fbin, dop, acquired) == (ref.code_phase, ref.doppler_bin, ref.doppler_hz, ref.acquired)
+    assert abs(peak - ref.peak) <= 1e-12 * ref.peak and abs(snr - ref.snr_db) <= 1e-9

@@ -422,6 +422,55 @@ def test_sweep_from_a_recording_file(tmp_path):
     assert_rows_match(got[0], oracle.coarse_search(oracle.read_if_block(file, signal, 2), signal, acq, prns), what="sweep_file window 0")
 
 
+@pytest.mark.parametrize("prns,world", [([1, 3, 7, 16, 22, 30], 2), ([1, 3, 7, 16, 22, 30], 4), ([1, 3, 7, 16, 22, 30], 8),
+                                        ([7], 4), ([3, 22], 5), ([7], 48)])
+def test_peer_memory_exchange_shards_give_the_single_gpu_bytes(prns, world):
+    """gnssacq_xchg_* (SURVEY 8e): one acquisition dealt out to `world` shards -- whole PRNs, or Doppler-bin ranges
+    when there are fewer PRNs than shards --, candidates written into the root's table, K4 on the root over the full
+    grid: the rows are byte for byte the single-handle search's.  (One GPU here: the shards run one after the other;
+    on a multi-GPU box they run concurrently -- bench.py --gpus N.)"""
+    from gnssacq.dist import LocalMultiGpu
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=3)
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 3)
+    cfg = cfg_from(file, signal, acq, prns)
+    with api.Searcher(cfg) as s:
+        want = [bytes(r) for r in s.search(raw_b)]
+    with LocalMultiGpu(cfg, [0] * world) as m:
+        assert m.serial
+        got = m.search(raw_b)
+        again = m.search(raw_b)
+        st = m.searchers[0].last_stats
+    assert [bytes(r) for r in got] == want
+    assert [bytes(r) for r in again] == want
+    assert st.gather_wait_ms >= 0.0
+    assert_rows_match(got, oracle_rows(raw_b, file, signal, acq, prns), what=f"xchg world={world}")
+
+
+def test_bin_range_handle_alone():
+    """A handle that owns bins [b0, b0+n) of the grid (config.bin_first / bin_count) reports its winner in FULL-grid
+    bin indices and produces the full search's candidates for those bins (same forward bases)."""
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 2)
+    with api.Searcher(cfg_from(file, signal, acq, [3])) as s:
+        full = s.search(raw_b)[0]
+    lo = max(full.doppler_bin - 3, 0)
+    cfg = cfg_from(file, signal, acq, [3])
+    cfg.bin_first, cfg.bin_count = lo, 7
+    with api.Searcher(cfg) as s:
+        part = s.search(raw_b)[0]
+    assert bytes(part) == bytes(full)                                  # the winner's bin is inside the range
+    cfg.bin_first, cfg.bin_count = 0, 2                               # a range without the winner: its own best row
+    with api.Searcher(cfg) as s:
+        other = s.search(raw_b)[0]
+    assert other.doppler_bin in (0, 1) and other.peak <= full.peak
+    bad = cfg_from(file, signal, acq, [3])
+    bad.bin_first, bad.bin_count = 40, 2
+    with pytest.raises(gnssacq.GnssAcqError):
+        api.Searcher(bad)
+
+
 def test_fetch_follows_the_last_search_output():
     """gnssacq_fetch_results returns the rows of the LAST enqueued search also when that search wrote them into a
     caller-owned device buffer (gnssacq_enqueue_device_out), and accepts out == NULL for timings only."""
