@@ -366,7 +366,15 @@ struct SearchLoader {
         return c;
     }
     template <int Q, int C>
-    GNSS_HD cf at(const Ctx& c) const { return cmul_scalar(ld_ro(c.pc + C * 125), ld_ro(c.px + C * 125)); }
+    GNSS_HD cf at(const Ctx& c) const {
+#if defined(GNSS_EXPERIMENT_NOCC)      // timing only (wrong results): no code-spectrum traffic
+        return cmul_scalar(mk(1.0f + (float)C, 0.5f), ld_ro(c.px + C * 125));
+#elif defined(GNSS_EXPERIMENT_NOX)     // timing only: no forward-spectrum traffic
+        return cmul_scalar(ld_ro(c.pc + C * 125), mk(1.0f + (float)C, 0.5f));
+#else
+        return cmul_scalar(ld_ro(c.pc + C * 125), ld_ro(c.px + C * 125));
+#endif
+    }
     template <int Q>
     GNSS_HD void load(int a, int b, cf (&z)[Q]) const {
         const int as = (a - sa) & 15;
