@@ -21,7 +21,7 @@
 
 using namespace gnss;
 
-#define GNSSACQ_VERSION_STR "gnssacq 0.1.0 (sm_100a)"
+#define GNSSACQ_VERSION_STR "gnssacq 0.2.0 (sm_100a)"
 
 namespace {
 

@@ -2,17 +2,23 @@
 """bench.py -- search cells/s of the 32-PRN parallel code-phase acquisition (BASELINE.json metric).
 
 A *step* is one complete coarse acquisition (acquisition.m:27-80 minus file I/O) of one synthetic IF
-block of the chosen BASELINE config: wipe-off + forward FFT of every (base, block), the
+block of the chosen BASELINE config: K1a/K1b (re-order, wipe-off, forward FFT of every (base, block)), the
 (PRN x Doppler bin x block) correlation search with on-chip non-coherent accumulation, row peaks and
 the per-PRN decision.  cells = PRNs x Doppler bins x code phases (independent of K).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|3|4|5] [--impl reference]
 
-N > 1: launched by torchrun, one rank per GPU; PRN-major shards, IF block broadcast from rank 0 and the
-result rows all-gathered over NCCL inside every step (strong scaling of one acquisition).
+Default workload: config 1, the Opensky-shaped block of BASELINE.json's north_star target.  The line carries
+`value` (device-resident input, CUDA events), `e2e` (N = 1: through gnssacq_search with a pageable host buffer,
+the call the MEX gateway makes; config 4: one gnssacq_sweep_file over `steps` epochs of a recording file),
+`roofline`, `cpu_baseline`, `clocks` and `parity_checked` (the rows just timed, against the oracle on a PRN subset).
+N > 1: launched by torchrun, one rank per GPU; ONE acquisition is sharded over the ranks (whole PRNs, or Doppler
+bins when there are fewer PRNs than GPUs) and exchanged through peer memory inside every step -- the IF block is
+pulled from rank 0 over NVLink by K1a, the candidates are stored into rank 0's table by K2, K4 runs on rank 0
+(strong scaling of one acquisition; `--xchg nccl` = the r01 NCCL broadcast + all-gather instead).
 `--impl reference` times the CPU restatement of acquisition.m (oracle/, NumPy float64, literal 3-FFT
-loop) on all host cores: MATLAB/Octave do not exist in this image, so the oracle port is the
-reference arm (cpu_baseline.kind = "port").
+loop) on all host cores, a FULL acquisition per step for configs 1 and 2: MATLAB/Octave do not exist in this
+image, so the oracle port is the reference arm (cpu_baseline.kind = "port").
 """
 from __future__ import annotations
 
