@@ -100,6 +100,26 @@ def test_null_arguments_are_errors_not_crashes():
     assert api.lib.gnssacq_correlate(None, 0, None, 0, None, None, None) == -1
     assert api.lib.gnssacq_track(None, 0, None, None, 0, None) == -1
     assert api.lib.gnssacq_loop_params_default(None) == -1
+    assert api.lib.gnssacq_sweep_file(None, b"/nonexistent", 0, 100, 1, None, None) == -1
+    assert api.lib.gnssacq_fetch_results(None, None, None) == -1
+    # the multi-GPU exchange: no handle -> state / argument errors, never a crash
+    assert api.lib.gnssacq_shard_plan(None, 0, 1, None, None) == -1
+    assert api.lib.gnssacq_xchg_root(None, None, None) == -1
+    assert api.lib.gnssacq_xchg_attach(None, None, None) == -1
+    assert api.lib.gnssacq_xchg_attach_local(None, None, None) == -1
+    assert not api.lib.gnssacq_xchg_if_buffer(None)
+    assert api.lib.gnssacq_xchg_enqueue(None, None, 0) == -7
+    assert api.lib.gnssacq_xchg_finish(None) == -7
+    assert api.lib.gnssacq_xchg_fetch(None, None, None) == -7
+    full = gnssacq.make_config(prns=[1, 2, 3])
+    mine, sh = api.Config(), api.Shard()
+    assert api.lib.gnssacq_shard_plan(C.byref(full), 3, 3, C.byref(mine), C.byref(sh)) == -1      # rank out of range
+    assert api.lib.gnssacq_shard_plan(C.byref(full), 0, 63, C.byref(mine), C.byref(sh)) == -1     # more shards than flag words
+    full.bin_first, full.bin_count = 2, 5
+    assert api.lib.gnssacq_shard_plan(C.byref(full), 0, 2, C.byref(mine), C.byref(sh)) == -1      # wants the full grid
+    bad = gnssacq.make_config(prns=[1], bin_first=40, bin_count=5)                                  # 41-bin grid
+    h = C.c_void_p()
+    assert api.lib.gnssacq_create(C.byref(bad), C.byref(h)) == -1 and not h.value
     lp = api.LoopParams()
     assert api.lib.gnssacq_loop_params_default(C.byref(lp)) == 0
     assert (lp.dll_bw, lp.dll_damp, lp.dll_gain, lp.pll_bw, lp.pll_damp, lp.pll_gain, lp.spacing_chips) == (2.0, 0.707, 0.1, 15.0, 0.707, 0.25, 0.5)   # initParameters.m:59-65
