@@ -69,6 +69,7 @@ class PeerShard:
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
+        self._dist = dist
         torch.cuda.set_device(device)
         full = api.Config.from_buffer_copy(bytes(cfg_full))
         full.device = device
@@ -122,8 +123,16 @@ class PeerShard:
         return self.searcher.xchg_fetch(rows=(self.rank == 0))
 
     def close(self) -> None:
+        """The other ranks unmap the root's exchange block BEFORE the root frees it."""
+        if self.rank != 0 and self.searcher:
+            self.searcher.close()
+            self.searcher = None
+        if self.world > 1 and self._dist is not None:
+            self.torch.cuda.synchronize()
+            self._dist.barrier()
         if self.searcher:
             self.searcher.close()
+            self.searcher = None
 
 
 class _DevArray:
