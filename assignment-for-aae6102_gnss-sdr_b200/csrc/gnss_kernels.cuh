@@ -799,10 +799,21 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         // pass 4 of this block and pass 3 of the next share a barrier interval: the L2 latency of the
         // former hides under the arithmetic of the latter.  (Moving pass 3 in front of the group
         // barrier to add slack was measured in r01 and lost 3 %.)
-        for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
-        GNSS_TL(9);
-        if (more)
-            for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
+        // The two are independent inside the interval, so half of the warps (1 and 2 of every four) run them in the
+        // opposite order: while the others wait for pass 4's L2 loads these issue pass 3's arithmetic, and vice versa
+        // (one copy of each body; the order is a runtime switch, not duplicated code).  Measured r02, same box:
+        // 7.05 -> 6.87 ms / 3.09 -> 2.96 ms; warp parity or the upper half as the flipped set are within 1 % of it
+        // (profiles/r02/ab_flip_v14.txt).  A CTA whose warps all sit in the same phase uses the FMA pipe and the
+        // L1 data pipe in turns; the flip takes a little of that lockstep away.
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int flip = (((tid >> 5) + 1) >> 1) & 1;
+            if ((half ^ flip) == 0) {
+                for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
+            } else if (more) {
+                for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
+            }
+        }
         GNSS_TL(10);
         if (later) {
             // A later part of a tail row that an earlier group finishes: publish this block's power plane on
