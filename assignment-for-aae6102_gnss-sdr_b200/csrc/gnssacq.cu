@@ -124,55 +124,14 @@ __device__ __forceinline__ void flag_wait_sys(const unsigned* p, unsigned epoch,
         __nanosleep(200);
     }
 }
-// Relay of the IF block (multi-GPU, >= 3 shards): the tiles of K1a's grid are dealt out to the shards in contiguous
-// slices; every non-root shard first copies ITS slice out of the root's HBM into a mirror buffer of its own
-// (relay_pull_kernel), and K1a then takes each tile from the shard that owns its slice -- the root sends every byte
-// roughly twice instead of (shards - 1) times, the rest crosses NVLink between the other GPUs in parallel.
-constexpr int kRelayMax = 16;
-struct CombRelay {
-    int world;                                   // 0: no relay (everything from `raw`)
-    int tiles_total;
-    const unsigned char* base[kRelayMax];        // per slice owner: where its slice can be read
-    const unsigned* flag[kRelayMax];             // per slice owner: "slice ready" word to wait for (nullptr: no wait)
-};
-__device__ __forceinline__ int relay_owner(int tile, int world, int tiles_total) {
-    return (int)(((long long)tile * world) / tiles_total);
-}
-__global__ void __launch_bounds__(256) relay_pull_kernel(const unsigned char* __restrict__ root_if, unsigned char* __restrict__ mirror,
-                                                         int rows_per_ms, int bps, int tiles_per_ms, int first_tile,
-                                                         const unsigned* root_ready, unsigned epoch, unsigned* my_flag,
-                                                         unsigned* ticket, unsigned* timeout) {
-    if (threadIdx.x == 0) flag_wait_sys(root_ready, epoch, timeout);
-    __syncthreads();
-    const int t = first_tile + blockIdx.x;
-    const int ms = t / tiles_per_ms, tile = t - ms * tiles_per_ms;
-    const int m0 = tile * kCombTM, tm = min(kCombTM, rows_per_ms - m0);
-    const size_t off = ((size_t)ms * rows_per_ms + m0) * 16 * bps;
-    const uint4* src = reinterpret_cast<const uint4*>(root_if + off);
-    uint4* dst = reinterpret_cast<uint4*>(mirror + off);
-    for (int i = threadIdx.x; i < tm * bps; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {        // the last CTA of the slice publishes it
-            *ticket = 0;
-            flag_store_sys(my_flag, epoch);
-        }
-    }
-}
 __global__ void __launch_bounds__(256) comb_kernel(const unsigned char* __restrict__ raw, unsigned char* __restrict__ out,
                                                    int rows_per_ms /* N/16 */, int bps, int pitch, int tiles_per_ms,
                                                    unsigned* flag_publish, const unsigned* flag_wait, unsigned epoch,
-                                                   unsigned* timeout, CombRelay relay) {
+                                                   unsigned* timeout) {
     extern __shared__ __align__(16) unsigned smem_w[];       // [TM][4*bps + 1] words (one pad word per m: conflict-free column reads)
     // multi-GPU: the root announces that its IF buffer holds this step's block (it does, by stream order);
     // every other shard waits for that before pulling the block out of the root's HBM
     if (flag_publish && blockIdx.x == 0 && threadIdx.x == 0) flag_store_sys(flag_publish, epoch);
-    if (relay.world > 0) {
-        const int s = relay_owner(blockIdx.x, relay.world, relay.tiles_total);
-        raw = relay.base[s];
-        flag_wait = relay.flag[s];
-    }
     if (flag_wait) {
         if (threadIdx.x == 0) flag_wait_sys(flag_wait, epoch, timeout);
         __syncthreads();
@@ -652,12 +611,6 @@ struct gnssacq_handle {
         gnssacq_result* h_res_all = nullptr;   // root, pinned
         unsigned epoch = 0;
         cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
-        // relay of the IF block between the non-root shards (optional, gnssacq_xchg_relay_*)
-        unsigned char* mirror = nullptr;       // own: [if_span bytes][64 flag words: 0 = slice ready, 1 = ticket]
-        unsigned char* peer_mirror[16] = {};   // the other shards' mirrors (mapped); [rank] = own
-        bool peer_ipc[16] = {};
-        bool relay_on = false;
-        unsigned pulled_epoch = 0;             // the step whose slice is already in the mirror
     } xc;
     const gnssacq_result* d_last_rows = nullptr;   // where the last enqueued search wrote its rows (d_res or the caller's buffer)
     Candidate* d_row_slots = nullptr;
@@ -838,8 +791,6 @@ int gnssacq_destroy(gnssacq_handle* h) {
     if (h->xc.on) {
         if (h->xc.is_root) { cudaFree(h->xc.block); cudaFree(h->xc.d_prn_all); cudaFree(h->xc.d_res_all); if (h->xc.h_res_all) cudaFreeHost(h->xc.h_res_all); }
         else if (h->xc.ipc_opened) cudaIpcCloseMemHandle(h->xc.block);
-        for (int r = 0; r < 16; ++r) if (h->xc.peer_ipc[r]) cudaIpcCloseMemHandle(h->xc.peer_mirror[r]);
-        cudaFree(h->xc.mirror);
         for (cudaEvent_t e : {h->xc.ev_a, h->xc.ev_b, h->xc.ev_c, h->xc.ev_d}) if (e) cudaEventDestroy(e);
     }
     if (h->ev_upload) cudaEventDestroy(h->ev_upload);
@@ -1030,9 +981,6 @@ extern "C" int gnssacq_debug_timeline(unsigned long long* out /*[16*16*32]*/) {
     return cudaMemcpy(out, g_timeline, 16 * 16 * 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -4;
 }
 #endif
-static size_t xchg_if_span(const gnssacq_handle* h);
-static int relay_pull(gnssacq_handle* h, unsigned step);
-
 // Pageable caller memory -> HBM through the handle's pinned staging buffer, in chunks: the host copy of chunk i+1
 // overlaps the DMA of chunk i (one chunk of latency instead of the sum of both copies).  The caller's buffer is
 // free again when this returns.
@@ -1071,25 +1019,10 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
         const int bps = h->cfg.data_type * h->cfg.data_precision;
         const int rows = h->N / 16, tiles = (rows + kCombTM - 1) / kCombTM;
         if (xchg) CU(cudaEventRecord(xc.ev_a, s));
-        CombRelay relay{};
-        if (xchg && !xc.is_root && xc.relay_on) {
-            if (int rc = relay_pull(h, xc.epoch)) return rc;     // (no-op if gnssacq_xchg_relay_pull already ran for this step)
-            const int W = xc.sh.world;
-            relay.world = W;
-            relay.tiles_total = h->K * h->M * tiles;
-            for (int r = 0; r < W; ++r) {
-                if (r == 0) { relay.base[r] = xc.if_buf; relay.flag[r] = xc.flags; }
-                else if (r == xc.sh.rank) { relay.base[r] = xc.mirror; relay.flag[r] = nullptr; }    // own slice: stream order
-                else {
-                    relay.base[r] = xc.peer_mirror[r];
-                    relay.flag[r] = reinterpret_cast<const unsigned*>(xc.peer_mirror[r] + xchg_if_span(h));
-                }
-            }
-        }
         comb_kernel<<<h->K * h->M * tiles, 256, (size_t)kCombTM * (4 * bps + 1) * 4, s>>>(
             (const unsigned char*)d_if, h->d_comb, rows, bps, h->comb_pitch, tiles,
             (xchg && xc.is_root) ? xc.flags : nullptr, (xchg && !xc.is_root) ? xc.flags : nullptr, xc.epoch,
-            xchg ? xc.flags + 63 : nullptr, relay);
+            xchg ? xc.flags + 63 : nullptr);
         CU(cudaGetLastError());
         if (xchg) CU(cudaEventRecord(xc.ev_b, s));
         Wipe2Args w2;
@@ -1264,29 +1197,6 @@ static int xchg_common(gnssacq_handle* h, const gnssacq_shard* sh) {
     return GNSSACQ_OK;
 }
 static size_t xchg_if_span(const gnssacq_handle* h) { return (h->if_bytes + 255) / 256 * 256; }
-
-// phase A of the relay on a non-root shard: copy this shard's slice of step `step`'s IF block from the root into its
-// mirror.  Called from gnssacq_xchg_enqueue (step = the step being enqueued) or ahead of it through
-// gnssacq_xchg_relay_pull (step = the next one); the second call for the same step is a no-op.
-static int relay_pull(gnssacq_handle* h, unsigned step) {
-    auto& xc = h->xc;
-    if (!xc.relay_on || xc.is_root || xc.pulled_epoch == step) return GNSSACQ_OK;
-    const int bps = h->cfg.data_type * h->cfg.data_precision;
-    const int rows = h->N / 16, tiles = (rows + kCombTM - 1) / kCombTM, W = xc.sh.world;
-    const long long total = (long long)h->K * h->M * tiles;
-    // tiles t with floor(t * W / total) == rank
-    const int first = (int)((xc.sh.rank * total + W - 1) / W), last = (int)(((xc.sh.rank + 1) * total + W - 1) / W);
-    if (last > first) {
-        unsigned* fl = reinterpret_cast<unsigned*>(xc.mirror + xchg_if_span(h));
-        relay_pull_kernel<<<last - first, 256, 0, h->stream>>>(xc.if_buf, xc.mirror, rows, bps, tiles, first, xc.flags, step,
-                                                            fl, fl + 1, xc.flags + 63);
-        CU(cudaGetLastError());
-        h->launches += 1;
-    }
-    xc.pulled_epoch = step;
-    return GNSSACQ_OK;
-}
-
 static size_t xchg_cand_span(const gnssacq_shard* sh) {
     return ((size_t)sh->n_prn_total * sh->freq_num_total * sizeof(Candidate) + 255) / 256 * 256;
 }
@@ -1348,68 +1258,6 @@ int gnssacq_xchg_attach_local(gnssacq_handle* h, const gnssacq_shard* sh, gnssac
     }
     xchg_map(h, root->xc.block);
     return GNSSACQ_OK;
-}
-
-// ---- relay of the IF block between the non-root shards (optional; worthwhile from 3 shards on) ----
-static int relay_common(gnssacq_handle* h) {
-    if (!h || !h->xc.on) return fail(h, GNSSACQ_ERR_STATE, "no exchange set up on this handle");
-    if (h->xc.sh.world > kRelayMax) return fail(h, GNSSACQ_ERR_INVALID_ARG, "the relay supports up to 16 shards");
-    CU(cudaSetDevice(h->device));
-    return GNSSACQ_OK;
-}
-int gnssacq_xchg_relay_export(gnssacq_handle* h, void* ipc_out) {
-    if (int rc = relay_common(h)) return rc;
-    if (h->xc.is_root) { if (ipc_out) std::memset(ipc_out, 0, GNSSACQ_IPC_BYTES); return GNSSACQ_OK; }   // the root needs no mirror
-    if (!h->xc.mirror) {
-        const size_t bytes = xchg_if_span(h) + 64 * sizeof(unsigned);
-        CU(cudaMalloc(&h->xc.mirror, bytes));
-        CU(cudaMemset(h->xc.mirror, 0, bytes));
-    }
-    h->xc.peer_mirror[h->xc.sh.rank] = h->xc.mirror;
-    if (ipc_out) {
-        cudaIpcMemHandle_t ih;
-        CU(cudaIpcGetMemHandle(&ih, h->xc.mirror));
-        std::memset(ipc_out, 0, GNSSACQ_IPC_BYTES);
-        std::memcpy(ipc_out, &ih, sizeof ih);
-    }
-    return GNSSACQ_OK;
-}
-int gnssacq_xchg_relay_attach(gnssacq_handle* h, const void* ipc_all) {
-    if (int rc = relay_common(h)) return rc;
-    if (h->xc.is_root) return GNSSACQ_OK;
-    if (!ipc_all || !h->xc.mirror) return fail(h, GNSSACQ_ERR_STATE, "gnssacq_xchg_relay_export first");
-    for (int r = 1; r < h->xc.sh.world; ++r) {
-        if (r == h->xc.sh.rank || h->xc.peer_mirror[r]) continue;
-        cudaIpcMemHandle_t ih;
-        std::memcpy(&ih, static_cast<const unsigned char*>(ipc_all) + (size_t)r * GNSSACQ_IPC_BYTES, sizeof ih);
-        void* p = nullptr;
-        CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
-        h->xc.peer_mirror[r] = static_cast<unsigned char*>(p);
-        h->xc.peer_ipc[r] = true;
-    }
-    h->xc.relay_on = true;
-    return GNSSACQ_OK;
-}
-int gnssacq_xchg_relay_attach_local(gnssacq_handle* h, gnssacq_handle* const* shards) {
-    if (int rc = relay_common(h)) return rc;
-    if (h->xc.is_root) return GNSSACQ_OK;
-    if (!shards || !h->xc.mirror) return fail(h, GNSSACQ_ERR_STATE, "gnssacq_xchg_relay_export first");
-    for (int r = 1; r < h->xc.sh.world; ++r) {
-        if (r == h->xc.sh.rank) continue;
-        if (!shards[r] || !shards[r]->xc.mirror) return fail(h, GNSSACQ_ERR_INVALID_ARG, "every non-root shard must have exported its mirror");
-        if (shards[r]->device != h->device) {
-            const cudaError_t e = cudaDeviceEnablePeerAccess(shards[r]->device, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
-            cudaGetLastError();
-        }
-        h->xc.peer_mirror[r] = shards[r]->xc.mirror;
-    }
-    h->xc.relay_on = true;
-    return GNSSACQ_OK;
-}
-int gnssacq_xchg_relay_pull(gnssacq_handle* h) {
-    if (int rc = relay_common(h)) return rc;
-    return relay_pull(h, h->xc.epoch + 1);
 }
 
 void* gnssacq_xchg_if_buffer(gnssacq_handle* h) { return (h && h->xc.on && h->xc.is_root) ? h->xc.if_buf : nullptr; }

@@ -111,7 +111,6 @@ EXPORTS = (
     "gnssacq_loop_params_default", "gnssacq_track",
     "gnssacq_shard_plan", "gnssacq_xchg_root", "gnssacq_xchg_attach", "gnssacq_xchg_attach_local",
     "gnssacq_xchg_if_buffer", "gnssacq_xchg_enqueue", "gnssacq_xchg_finish", "gnssacq_xchg_fetch",
-    "gnssacq_xchg_relay_export", "gnssacq_xchg_relay_attach", "gnssacq_xchg_relay_attach_local", "gnssacq_xchg_relay_pull",
 )
 
 
@@ -152,10 +151,6 @@ def _load() -> C.CDLL:
     lib.gnssacq_xchg_root.argtypes = [vp, C.POINTER(Shard), vp]
     lib.gnssacq_xchg_attach.argtypes = [vp, C.POINTER(Shard), vp]
     lib.gnssacq_xchg_attach_local.argtypes = [vp, C.POINTER(Shard), vp]
-    lib.gnssacq_xchg_relay_export.argtypes = [vp, vp]
-    lib.gnssacq_xchg_relay_attach.argtypes = [vp, vp]
-    lib.gnssacq_xchg_relay_attach_local.argtypes = [vp, C.POINTER(vp)]
-    lib.gnssacq_xchg_relay_pull.argtypes = [vp]
     lib.gnssacq_xchg_if_buffer.argtypes = [vp]
     lib.gnssacq_xchg_if_buffer.restype = vp
     lib.gnssacq_xchg_enqueue.argtypes = [vp, vp, C.c_size_t]
@@ -353,21 +348,6 @@ class Searcher:
     def xchg_attach_local(self, shard: "Shard", root: "Searcher") -> None:
         self._check(lib.gnssacq_xchg_attach_local(self._h, C.byref(shard), root._h))
         self.shard = shard
-
-    def xchg_relay_export(self) -> bytes:
-        buf = C.create_string_buffer(IPC_BYTES)
-        self._check(lib.gnssacq_xchg_relay_export(self._h, buf))
-        return buf.raw
-
-    def xchg_relay_attach(self, ipc_all: Sequence[bytes]) -> None:
-        self._check(lib.gnssacq_xchg_relay_attach(self._h, C.c_char_p(b"".join(ipc_all))))
-
-    def xchg_relay_attach_local(self, shards: Sequence[Optional["Searcher"]]) -> None:
-        hs = (C.c_void_p * len(shards))(*[(s._h if s else None) for s in shards])
-        self._check(lib.gnssacq_xchg_relay_attach_local(self._h, hs))
-
-    def xchg_relay_pull(self) -> None:
-        self._check(lib.gnssacq_xchg_relay_pull(self._h))
 
     def xchg_if_buffer(self) -> int:
         return int(lib.gnssacq_xchg_if_buffer(self._h) or 0)

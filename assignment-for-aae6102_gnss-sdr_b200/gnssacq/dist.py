@@ -65,7 +65,7 @@ class PeerShard:
     there are fewer PRNs than GPUs (then the Doppler bins are split).  `torch.distributed` is used once, to
     hand rank 0's CUDA IPC handle to the other processes.  No CPU fallback."""
 
-    def __init__(self, cfg_full: api.Config, rank: int, world: int, device: int, dist=None, relay: bool = True):
+    def __init__(self, cfg_full: api.Config, rank: int, world: int, device: int, dist=None):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
@@ -87,16 +87,6 @@ class PeerShard:
             dist.broadcast_object_list(ipc, src=0)
         if rank != 0 and self.searcher:
             self.searcher.xchg_attach(self.shard, ipc[0])
-        # from 3 shards on: relay the IF block between the non-root ranks (each pulls one slice from rank 0, the rest
-        # from its peers) -- only when every rank owns rows, i.e. takes part in every step
-        self.relay = False
-        if relay and 3 <= world <= 16:
-            mine_ipc = self.searcher.xchg_relay_export() if self.searcher else None
-            all_ipc = [None] * world
-            dist.all_gather_object(all_ipc, mine_ipc)
-            if all(h is not None for h in all_ipc):
-                self.searcher.xchg_relay_attach(all_ipc)
-                self.relay = True
         self.d_if_ptr = self.searcher.xchg_if_buffer() if rank == 0 else 0
 
     def bind_stream(self) -> None:
@@ -157,7 +147,7 @@ class LocalMultiGpu:
     torchrun).  If several shards share a device (tests on a one-GPU box), the steps are serialised with host
     syncs, because kernels of different shards that wait for one another must not share a GPU."""
 
-    def __init__(self, cfg_full: api.Config, devices: Sequence[int], relay: bool = True):
+    def __init__(self, cfg_full: api.Config, devices: Sequence[int]):
         self.world = len(devices)
         self.serial = len(set(devices)) < len(devices)
         self.searchers: List[api.Searcher] = []
@@ -173,22 +163,12 @@ class LocalMultiGpu:
         for s, sh in zip(self.searchers[1:], self.shards[1:]):
             if s:
                 s.xchg_attach_local(sh, root)
-        self.relay = relay and 3 <= self.world <= 16 and all(s is not None for s in self.searchers)
-        if self.relay:
-            for s in self.searchers:
-                s.xchg_relay_export()
-            for s in self.searchers:
-                s.xchg_relay_attach_local(self.searchers)
 
     def search(self, if_bytes) -> List[api.Result]:
         root = self.searchers[0]
         root.xchg_enqueue(if_bytes)
         if self.serial:
             root.xchg_fetch(rows=False)
-            if self.relay:                      # one GPU: phase A of every shard must be over before any phase B starts
-                for s in self.searchers[1:]:
-                    s.xchg_relay_pull()
-                    s.xchg_fetch(rows=False)
         for s in self.searchers[1:]:
             if s:
                 s.xchg_enqueue(None)

@@ -203,17 +203,6 @@ int gnssacq_shard_plan(const gnssacq_config* full, int32_t rank, int32_t world, 
 int gnssacq_xchg_root(gnssacq_handle* root, const gnssacq_shard* shard, void* ipc_out);
 int gnssacq_xchg_attach(gnssacq_handle* h, const gnssacq_shard* shard, const void* root_ipc);        /* other process */
 int gnssacq_xchg_attach_local(gnssacq_handle* h, const gnssacq_shard* shard, gnssacq_handle* root); /* same process */
-/* Optional, from 3 shards on: RELAY the IF block between the non-root shards instead of having every one of them pull
- * all of it from the root (whose NVLink egress is then the bottleneck: (world-1) x the block).  Every non-root shard owns
- * one slice of the block: it copies that slice from the root into a mirror buffer of its own (phase A) and K1a takes
- * every other slice from the shard that owns it (phase B), so the root sends each byte about twice and the rest crosses
- * NVLink between the other GPUs in parallel.  Set-up, after gnssacq_xchg_attach: every shard exports (root: no-op, zeros),
- * the world x GNSSACQ_IPC_BYTES handles are gathered in rank order, every shard attaches.  Rows are unaffected.
- * gnssacq_xchg_relay_pull runs phase A of the NEXT step ahead of gnssacq_xchg_enqueue (which otherwise does it itself). */
-int gnssacq_xchg_relay_export(gnssacq_handle* h, void* ipc_out);
-int gnssacq_xchg_relay_attach(gnssacq_handle* h, const void* ipc_all /* world x GNSSACQ_IPC_BYTES, entry r = shard r */);
-int gnssacq_xchg_relay_attach_local(gnssacq_handle* h, gnssacq_handle* const* shards /* world, same process */);
-int gnssacq_xchg_relay_pull(gnssacq_handle* h);
 /* device pointer of the root's IF buffer (gnssacq_if_bytes): for callers whose samples are already in HBM */
 void* gnssacq_xchg_if_buffer(gnssacq_handle* root);
 /* one step of this shard.  host_if: root only -- NULL = the IF block is already in the exchange block's buffer,

@@ -438,14 +438,11 @@ def test_peer_memory_exchange_shards_give_the_single_gpu_bytes(prns, world):
         want = [bytes(r) for r in s.search(raw_b)]
     with LocalMultiGpu(cfg, [0] * world) as m:
         assert m.serial
-        assert m.relay == (world >= 3 and world <= len(prns) * 41 and world <= 16)   # IF block relayed between the non-root shards
         got = m.search(raw_b)
         again = m.search(raw_b)
         st = m.searchers[0].last_stats
     assert [bytes(r) for r in got] == want
     assert [bytes(r) for r in again] == want
-    with LocalMultiGpu(cfg, [0] * world, relay=False) as m:             # every shard pulls the whole block from the root
-        assert [bytes(r) for r in m.search(raw_b)] == want
     assert st.gather_wait_ms >= 0.0
     assert_rows_match(got, oracle_rows(raw_b, file, signal, acq, prns), what=f"xchg world={world}")
 
