@@ -1,6 +1,6 @@
 #!/bin/bash
 # r02: ncu launch lists (every launch with its device time) and one full capture of the search kernel, configs 1 and 2.
-O=gpurun_out/r02p; mkdir -p $O
+O=gpurun_out/r02p14; mkdir -p $O
 for C in 1 2; do
   CMD="python bench.py --config $C --steps 2 --warmup 1 --no-cpu --no-parity"
   $CMD > $O/plain_c$C.log 2>&1 && \
