@@ -32,6 +32,7 @@ struct SearchArgs {
     Candidate* row_slots;  // coop variant: [groups][R] per-CTA partial row results
     float* partial;        // coop variant: [groups][K-1][R][ACC_ELEMS] power planes of tail-row blocks handed to the finishing group
     unsigned* part_ctr;    // coop variant: [groups][R] published planes (zeroed before the launch)
+    unsigned* row_ticket;  // coop variant: [groups] row-end tickets: the last of a group's R CTAs to finish a row writes its candidate
     int row_granular;      // coop variant: deal out whole rows only (no hand-over; sums independent of the group count)
 #ifdef GNSS_TIMELINE       // experiment builds only (profiles/timeline.py): clock64 stamps of one iteration of group 0
     unsigned long long* timeline;   // [R][warps][32]

@@ -917,12 +917,18 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             float dv = -1.f;
             int dm = INT_MAX;
             block_reduce<T>(dv, dm, wsum, rs);
-            target += R;
+            // Every thread has read its window cells (block_reduce ends with a CTA barrier): the accumulator can be
+            // cleared while thread 0 finishes the row.  No second group barrier: each CTA publishes its two partial sums
+            // and takes a ticket (acq_rel); the LAST of the R CTAs to do so adds the partials IN RANK ORDER (bit-identical
+            // whichever CTA that is) and writes the candidate.  Nobody waits for anybody here.  The slots are not touched
+            // again before the next row end, and every block in between has a group barrier that the finisher joins
+            // only after this.
+            for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
             if (tid == 0) {
                 slots[rank].sum_win = wsum;
-                group_arrive(ctr);
-                group_spin(ctr, target);
-                if (rank == 0) {
+                unsigned old;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.row_ticket + group) : "memory");
+                if ((old + 1) % R == 0) {
                     double s_all = 0.0, s_win = 0.0;
                     for (int r = 0; r < R; ++r) {
                         s_all += __ldcg(&slots[r].sum_all);
@@ -936,8 +942,6 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
                     a.cand[(size_t)p * a.cand_stride + b] = c;
                 }
             }
-            __syncthreads();
-            for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
             // (the next write to acc is pass 4 of the next block, several CTA barriers away)
         }
         if (!more) break;

@@ -925,7 +925,7 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         CUC(cudaMalloc(&h->d_scratch, (size_t)n * ops->scratch_bytes_per_cluster));
         // the padding columns of the exchange layout are never written: they must read as exact zeros
         CUC(cudaMemsetAsync(h->d_scratch, 0, (size_t)n * ops->scratch_bytes_per_cluster, h->stream));
-        CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * (1 + ops->R) * sizeof(unsigned)));     // group barriers + hand-over counters
+        CUC(cudaMalloc(&h->d_group_ctr, (size_t)n * (2 + ops->R) * sizeof(unsigned)));     // group barriers + hand-over counters + row tickets
         if (by_blocks) CUC(cudaMalloc(&h->d_partial, (size_t)n * (h->K - 1) * ops->partial_bytes_per_group));
         CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
@@ -1067,6 +1067,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.row_slots = h->d_row_slots;
     sa.partial = h->d_partial;
     sa.part_ctr = h->d_group_ctr ? h->d_group_ctr + h->coop_groups : nullptr;
+    sa.row_ticket = h->d_group_ctr ? h->d_group_ctr + (size_t)h->coop_groups * (1 + h->ops->R) : nullptr;
     sa.row_granular = h->d_partial ? 0 : 1;
 #ifdef GNSS_TIMELINE
     static unsigned long long* d_timeline = nullptr;
@@ -1076,7 +1077,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     g_timeline = d_timeline;
 #endif
     if (h->coop_groups > 0) {
-        CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * (1 + h->ops->R) * sizeof(unsigned), s));
+        CU(cudaMemsetAsync(h->d_group_ctr, 0, (size_t)h->coop_groups * (2 + h->ops->R) * sizeof(unsigned), s));
         CU(h->ops->launch_search_coop(sa, h->coop_groups, s));
     } else if (h->l2x_clusters > 0) {
         CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));
