@@ -111,7 +111,11 @@ GNSS_HD float cnorm_acc(cf a, float acc) {
 GNSS_HD float cnorm(cf a) { return a.x * a.x + a.y * a.y; }
 // read-only global load of one complex value (LDG.E.64.CONSTANT on the device)
 GNSS_HD cf ld_ro(const cf* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(GNSS_EXPERIMENT_LDNA)     // experiment: operands do not allocate in L1 (each line is used once)
+    float2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return mk(v.x, v.y);
+#elif defined(__CUDA_ARCH__)
     const float2 v = __ldg(reinterpret_cast<const float2*>(p));
     return mk(v.x, v.y);
 #else

@@ -419,6 +419,24 @@ struct PowerAccumStorer {
     }
 };
 
+// Register-resident accumulator of the cooperative search kernel (r02): every engine variant has at most
+// ONE pass-4 task per thread (P4_TASKS <= T), so the 2 x 16 accumulators of that task can stay in registers for all
+// K blocks of a row; shared memory sees them once per row (dump before the row end) instead of a read-modify-write
+// per block.
+struct RegAccumStorer {
+    float (&a0)[16];
+    float (&a1)[16];
+    template <int Q, int R>
+    GNSS_HD void store2x(int /*t*/, const cf (&w0)[16], const cf (&w1)[16]) {
+        static_for<0, 16>([&](auto i_) {
+            constexpr int I = decltype(i_)::value;
+            constexpr int AP = (I / 4) + 4 * (I % 4);
+            a0[AP] = cnorm_acc(w0[I], a0[AP]);
+            a1[AP] = cnorm_acc(w1[I], a1[AP]);
+        });
+    }
+};
+
 // ---- spectrum store (K0 / K1): write Y to global in G layout of the *next* transform ----
 struct SpectrumStorer {
     cf* __restrict__ out;

@@ -697,7 +697,30 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     Candidate* slots = a.row_slots + (size_t)group * R;
     unsigned target = 0;
     fill_tw125(tw, tid, T);
+    // Register-resident accumulator (r02): every variant has at most ONE pass-4 task per thread,
+    // so its 2 x 16 accumulators can live in registers for all K blocks of a row; shared memory sees them once per row
+    // (dump_acc before the row end) instead of a read-modify-write per block.  Used where the registers allow it:
+    // Q = 13 compiles to 124 registers without spills (config 2: 2.946 -> 2.899 ms, same-box A/B, rows byte-identical);
+    // at Q = 29 pass 1 already needs all 128 and the accumulators spill (6.82 -> 8.33 ms), so it keeps the shared-memory
+    // accumulator (profiles/r02/ab_regacc_v15.txt).
+    constexpr bool kRegAcc = (Q <= 13) && (SX::P4_TASKS <= T);
+    float racc0[16], racc1[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { racc0[q] = 0.f; racc1[q] = 0.f; }
+    RegAccumStorer rst{racc0, racc1};
     PowerAccumStorer st{acc};
+    // registers -> shared-memory accumulator (this thread's two columns), registers cleared
+    auto dump_acc = [&]() {
+        if constexpr (kRegAcc) {
+            if (tid < SX::P4_TASKS) {
+#pragma unroll
+                for (int ap = 0; ap < 16; ++ap) {
+                    *reinterpret_cast<float2*>(acc + ap * SX::CHX + 2 * tid) = make_float2(racc0[ap], racc1[ap]);
+                    racc0[ap] = 0.f; racc1[ap] = 0.f;
+                }
+            }
+        }
+    };
     const int n_rows = a.P * a.B;
     auto loader_of = [&](int row) {           // loader of block 0 of a row (two dependent table reads: once per row)
         const int p = row % a.P, b = row / a.P;
@@ -773,14 +796,24 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             cf z[Q];
             const bool has = tid < S::P1_TASKS;
             if (has) pass1_compute<Q, R>(tid, rank, ld, z);
+            // A thread's SECOND pass-1 task (variants with two a-rows per CTA) is computed ahead of the barrier as well where
+            // the registers allow it (Q = 13: 2 x 26): its loads and DFT-Q then overlap the other warps' pass 3 / pass 4
+            // instead of sitting between the two barriers (config 2: 2.893 -> 2.848 ms, profiles/r02/ab_p1x2_v16.txt).
+            constexpr bool kTwo = (Q <= 13) && (S::P1_TASKS > T) && (S::P1_TASKS <= 2 * T);
+            cf z2[kTwo ? Q : 1];
+            const bool has2 = kTwo && tid + T < S::P1_TASKS;
+            if constexpr (kTwo) { if (has2) pass1_compute<Q, R>(tid + T, rank, ld, z2); }
             GNSS_TL(1);
             GNSS_KSYNC();                          // every thread is done with pass 3 of the current block
             GNSS_TL(2);
             if (tid == 0) group_arrive(ctr);       // release (cumulative over the CTA barrier): its rows are in L2
             GNSS_TL(3);
             if (has) pass1_store<Q, R>(tid, z, D);
-            if constexpr (S::P1_TASKS > T)
+            if constexpr (kTwo) {
+                if (has2) pass1_store<Q, R>(tid + T, z2, D);
+            } else if constexpr (S::P1_TASKS > T) {
                 for (int t = tid + T; t < S::P1_TASKS; t += T) pass1_task<Q, R>(t, rank, ld, D);
+            }
             GNSS_TL(4);
             GNSS_KSYNC();
             GNSS_TL(5);
@@ -809,7 +842,11 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
         for (int half = 0; half < 2; ++half) {
             const int flip = (((tid >> 5) + 1) >> 1) & 1;
             if ((half ^ flip) == 0) {
-                for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
+                if constexpr (kRegAcc) {
+                    if (tid < SX::P4_TASKS) pass4_task_xt<Q, R>(tid, rank, buf, rst);
+                } else {
+                    for (int t = tid; t < SX::P4_TASKS; t += T) pass4_task_xt<Q, R>(t, rank, buf, st);
+                }
             } else if (more) {
                 for (int t = tid3; t < S::P3_TASKS; t += T) pass3_task_xt<Q, R>(t, D, nbuf + (size_t)rank * S::A * GX::RSX);
             }
@@ -825,12 +862,14 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             int gf = group - 1;                    // the finisher: last group whose range starts at or before the row's
             while (tb(gf) > (cp.row - tail_base) * a.K) --gf;
             float* dst = a.partial + (((size_t)gf * (a.K - 1) + (kk - 1)) * R + rank) * SX::ACC_ELEMS;
+            dump_acc();                            // (publish_plane moves the columns of the thread's own task: program order)
             publish_plane<Q, R, T>(acc, dst, tid);
             if (last_of_part) {
                 __syncthreads();
                 if (tid == 0) group_arrive_n(a.part_ctr + (size_t)gf * R + rank, (unsigned)(cp.ke - cp.kb));   // release
             }
         } else if (last_of_part) {
+            dump_acc();
             __syncthreads();                       // this group's blocks of the row are in the accumulator
             const Part cp = part(i);
             const int row = cp.row;
@@ -923,7 +962,8 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             // whichever CTA that is) and writes the candidate.  Nobody waits for anybody here.  The slots are not touched
             // again before the next row end, and every block in between has a group barrier that the finisher joins
             // only after this.
-            for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
+            if constexpr (!kRegAcc)                // (register accumulators: every cell is overwritten by the next dump)
+                for (int e = tid; e < SX::ACC_ELEMS; e += T) acc[e] = 0.f;
             if (tid == 0) {
                 slots[rank].sum_win = wsum;
                 unsigned old;

@@ -18,12 +18,14 @@ for which in ("urban", "opensky"):
     spec, fs, if_hz = (urban_recording(), 26e6, 0.0) if which == "urban" else (opensky_recording(), 58e6, 4.58e6)
     raw = spec.read(0, 20)
     for n in prns:
-        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}))) as s:
+        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}), **({'threads': int(os.environ['AB_THREADS'])} if os.environ.get('AB_THREADS') and which == 'opensky' else {}))) as s:
             best = 1e9
             for _ in range(8):
-                s.search(raw)
+                rows = s.search(raw)
                 best = min(best, s.last_stats.search_ms)
-        print(which, n, round(best, 4), flush=True)
+            import hashlib, ctypes
+            digest = hashlib.sha1(b"".join(ctypes.string_at(ctypes.addressof(r), ctypes.sizeof(r)) for r in rows)).hexdigest()[:10]
+        print(which, n, round(best, 4), digest, flush=True)
 '''
 
 libs = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and not a.startswith("--")]
@@ -35,20 +37,27 @@ for i, a in enumerate(sys.argv):
     if a == "--rounds":
         rounds = int(sys.argv[i + 1])
 best = {}
+digests = {}
 for r in range(rounds):
     for name, path in libs:
         env = dict(os.environ, AB_LIB=os.path.abspath(path.split("@")[0]))
-        if "@" in path:                                  # name=lib.so@1 -> work_split=1
-            env["AB_WORK_SPLIT"] = path.split("@")[1]
+        if "@" in path:                                  # name=lib.so@1 -> work_split=1 ; name=lib.so@@160 -> threads=160 (opensky)
+            parts = path.split("@")
+            if parts[1]:
+                env["AB_WORK_SPLIT"] = parts[1]
+            if len(parts) > 2 and parts[2]:
+                env["AB_THREADS"] = parts[2]
         out = subprocess.run([sys.executable, "-c", CHILD, prns], env=env, capture_output=True, text=True)
         if out.returncode:
             print(name, "FAILED", out.stderr[-500:])
             continue
         for line in out.stdout.split("\n"):
             if line.strip():
-                which, n, ms = line.split()
+                which, n, ms, digest = line.split()
                 key = (which, int(n), name)
                 best[key] = min(best.get(key, 1e9), float(ms))
+                digests[key] = digest          # result rows of the last search: equal digests = byte-identical tables
 for which in ("urban", "opensky"):
     for n in [int(x) for x in prns.split(",")]:
-        print(which, "prns", n, {name: best.get((which, n, name)) for name, _ in libs}, flush=True)
+        print(which, "prns", n, {name: best.get((which, n, name)) for name, _ in libs},
+              "rows", {name: digests.get((which, n, name)) for name, _ in libs}, flush=True)
