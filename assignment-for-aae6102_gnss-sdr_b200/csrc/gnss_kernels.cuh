@@ -703,7 +703,8 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
     // Q = 13 compiles to 124 registers without spills (config 2: 2.946 -> 2.899 ms, same-box A/B, rows byte-identical);
     // at Q = 29 pass 1 already needs all 128 and the accumulators spill (6.82 -> 8.33 ms), so it keeps the shared-memory
     // accumulator (profiles/r02/ab_regacc_v15.txt).
-    constexpr bool kRegAcc = (Q <= 13) && (SX::P4_TASKS <= T);
+    constexpr bool kRoomy = (T * MINB <= 512);            // 128 registers per thread available
+    constexpr bool kRegAcc = (Q <= 13) && kRoomy && (SX::P4_TASKS <= T);
     float racc0[16], racc1[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) { racc0[q] = 0.f; racc1[q] = 0.f; }
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(T, MINB) search_kernel_coop(SearchArgs a) {
             // A thread's SECOND pass-1 task (variants with two a-rows per CTA) is computed ahead of the barrier as well where
             // the registers allow it (Q = 13: 2 x 26): its loads and DFT-Q then overlap the other warps' pass 3 / pass 4
             // instead of sitting between the two barriers (config 2: 2.893 -> 2.848 ms, profiles/r02/ab_p1x2_v16.txt).
-            constexpr bool kTwo = (Q <= 13) && (S::P1_TASKS > T) && (S::P1_TASKS <= 2 * T);
+            constexpr bool kTwo = (Q <= 13) && kRoomy && (S::P1_TASKS > T) && (S::P1_TASKS <= 2 * T);
             cf z2[kTwo ? Q : 1];
             const bool has2 = kTwo && tid + T < S::P1_TASKS;
             if constexpr (kTwo) { if (has2) pass1_compute<Q, R>(tid + T, rank, ld, z2); }

@@ -18,7 +18,7 @@ for which in ("urban", "opensky"):
     spec, fs, if_hz = (urban_recording(), 26e6, 0.0) if which == "urban" else (opensky_recording(), 58e6, 4.58e6)
     raw = spec.read(0, 20)
     for n in prns:
-        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}), **({'threads': int(os.environ['AB_THREADS'])} if os.environ.get('AB_THREADS') and which == 'opensky' else {}))) as s:
+        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}), **({'threads': int(os.environ['AB_THREADS_' + which.upper()])} if os.environ.get('AB_THREADS_' + which.upper()) else {}))) as s:
             best = 1e9
             for _ in range(8):
                 rows = s.search(raw)
@@ -46,7 +46,9 @@ for r in range(rounds):
             if parts[1]:
                 env["AB_WORK_SPLIT"] = parts[1]
             if len(parts) > 2 and parts[2]:
-                env["AB_THREADS"] = parts[2]
+                env["AB_THREADS_OPENSKY"] = parts[2]
+            if len(parts) > 3 and parts[3]:          # name=lib.so@@160@160 -> threads for opensky, urban
+                env["AB_THREADS_URBAN"] = parts[3]
         out = subprocess.run([sys.executable, "-c", CHILD, prns], env=env, capture_output=True, text=True)
         if out.returncode:
             print(name, "FAILED", out.stderr[-500:])
