@@ -22,6 +22,7 @@ struct SearchArgs {
     const int* bin_base;   // [B] which base a bin derives from
     const int* bin_shift;  // [B] shift in FFT bins relative to that base
     int P, B, K;
+    int row_first, n_rows; // this launch searches rows [row_first, +n_rows) of the grid, row = b*P + p (all of them: 0, P*B)
     int w;                 // ceil(Fs/fc) (acquisition.m:66)
     Candidate* cand;       // [P][cand_stride]: row (p, b) at cand[p*cand_stride + b].  A shard of a multi-GPU search
                            // points this straight into the ROOT GPU's table (peer memory, NVLink stores)

@@ -87,7 +87,8 @@ __global__ void finalize_kernel(const Candidate* __restrict__ cand, int P, int B
     const long long cnt = (long long)max(cp1 - w, 0) + (long long)max(N - cp1 - w + 1, 0);   // :67-68 index set
     const double noise = (c.sum_all - c.sum_win) / (double)cnt;
     const double pk = (double)g;
-    const double snr = 10.0 * log10(pk * pk / noise);
+    // (g < 0: a row-range handle used alone that owns none of this PRN's rows -- nothing to report)
+    const double snr = g < 0.f ? nan("") : 10.0 * log10(pk * pk / noise);
     gnssacq_result r;
     r.prn = prn_ids[p];
     r.acquired = (snr >= thr) ? 1 : 0;                  // :70 (NaN compares false)
@@ -165,12 +166,11 @@ __global__ void xchg_done_kernel(unsigned* flag, unsigned epoch) {
     flag_store_sys(flag, epoch);
 }
 // root, before K4: every other shard has delivered this step's candidates
-__global__ void xchg_wait_kernel(const unsigned* done_flags, int world, int n_prn, int n_bins, unsigned epoch, unsigned* timeout) {
+__global__ void xchg_wait_kernel(const unsigned* done_flags, int world, unsigned long long has_rows, unsigned epoch, unsigned* timeout) {
     const int r = 1 + (int)threadIdx.x;
     if (r >= world) return;
-    // gnssacq_shard_plan: with fewer PRNs than shards the bins are split, and a shard may end up with none
-    const bool has_rows = n_prn >= world || n_bins / world > 0 || r < n_bins % world;
-    if (has_rows) flag_wait_sys(done_flags + r, epoch, timeout);
+    // with fewer PRNs (or rows) than shards a shard may end up with nothing to search: it never reports
+    if ((has_rows >> r) & 1ull) flag_wait_sys(done_flags + r, epoch, timeout);
 }
 
 // acquisition.m:30-32 -- per-component mean of the int16 I/Q block (exact integer sums).
@@ -597,6 +597,7 @@ struct gnssacq_handle {
     int coop_groups = 0;           // > 0: use the cluster-free cooperative kernel with this many CTA groups
     unsigned* d_group_ctr = nullptr;
     int bin0 = 0, B_full = 0;      // this handle's bins are [bin0, bin0 + B) of the B_full-bin grid
+    int row0 = 0, n_rows = 0;      // ... and of that P x B grid (row = bin * P + prn index) it searches rows [row0, row0 + n_rows)
     // multi-GPU exchange (gnssacq_xchg_*)
     struct Xchg {
         bool on = false, is_root = false;
@@ -724,6 +725,12 @@ int validate(const gnssacq_config* c, std::string& why) {
         if (c->prn[i] < 1 || c->prn[i] > 51) { why = "PRN outside 1..51"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->bin_count < 0 || c->bin_first < 0 || (c->bin_count > 0 && c->bin_first + c->bin_count > c->freq_num) ||
         (c->bin_count == 0 && c->bin_first != 0)) { why = "bin_first / bin_count outside the freq_num grid"; return GNSSACQ_ERR_INVALID_ARG; }
+    {
+        const long long grid = (long long)c->n_prn * (c->bin_count > 0 ? c->bin_count : c->freq_num);
+        if (c->row_first < 0 || c->row_count < 0 || (long long)c->row_first + c->row_count > grid || (c->row_count == 0 && c->row_first != 0)) {
+            why = "row_first / row_count outside the n_prn x bins grid"; return GNSSACQ_ERR_INVALID_ARG;
+        }
+    }
     if (c->work_split < 0 || c->work_split > 2) { why = "work_split must be 0 (auto), 1 (whole rows) or 2 (block-granular tail)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->exchange < 0 || c->exchange > 3) { why = "exchange must be 0 (auto), 1 (DSMEM), 2 (L2 + clusters) or 3 (L2 + cooperative groups)"; return GNSSACQ_ERR_INVALID_ARG; }
     if (c->samples_per_ms <= 0 || c->samples_per_ms % 2000 != 0) {
@@ -867,6 +874,8 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         h->bin_base = bb;
         h->bin_shift = bs;
     }
+    h->row0 = cfg->row_count > 0 ? cfg->row_first : 0;
+    h->n_rows = cfg->row_count > 0 ? cfg->row_count : h->P * h->B;
     const size_t N = (size_t)h->N;
     const size_t nb = h->base_freq.size();
 
@@ -912,10 +921,10 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         bool by_blocks = xmode == 3 && cfg->work_split != 1 && h->K > 1 && (unsigned long long)n * n * h->K < (1ull << 32) &&
                          (unsigned long long)n * (h->K - 1) * ops->partial_bytes_per_group <= (2ull << 30);
         if (by_blocks && cfg->work_split == 0) {
-            const long long rows = (long long)h->P * h->B, rounds = (rows + n - 1) / n;
+            const long long rows = h->n_rows, rounds = (rows + n - 1) / n;
             by_blocks = (double)(rounds * n - rows) >= 0.04 * (double)(rounds * n);
         }
-        const long long max_useful = by_blocks ? (long long)h->P * h->B * h->K : (long long)h->P * h->B;
+        const long long max_useful = by_blocks ? (long long)h->n_rows * h->K : (long long)h->n_rows;
         if (n > max_useful) n = (int)max_useful;
         if (n <= 0) {
             gnssacq_destroy(h);
@@ -940,6 +949,12 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
     CUC(cudaMemcpyAsync(h->d_bin_shift, h->bin_shift.data(), h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaMemcpyAsync(h->d_prn, cfg->prn, h->P * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaMemcpyAsync(h->d_base_freq, h->base_freq.data(), nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->n_rows < h->P * h->B) {
+        // a row range: the cells of the handle's own table that it never writes must not win K4's maximum
+        std::vector<Candidate> none((size_t)h->P * h->B, Candidate{-1.f, 0, 0.0, 0.0});
+        CUC(cudaMemcpyAsync(h->d_cand, none.data(), none.size() * sizeof(Candidate), cudaMemcpyHostToDevice, h->stream));
+        CUC(cudaStreamSynchronize(h->stream));
+    }
     {
         // K1 v2 (comb rows + cp.async staging) whenever its shared memory fits; otherwise the v1 gather kernel
         const int bps = h->cfg.data_type * h->cfg.data_precision;
@@ -1058,6 +1073,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     sa.bin_base = h->d_bin_base;
     sa.bin_shift = h->d_bin_shift;
     sa.P = h->P; sa.B = h->B; sa.K = h->K;
+    sa.row_first = h->row0; sa.n_rows = h->n_rows;
     sa.w = h->w;
     sa.cand = xchg ? xc.cand_all + (size_t)xc.sh.prn_first * xc.sh.freq_num_total + xc.sh.bin_first : h->d_cand;
     sa.cand_stride = xchg ? xc.sh.freq_num_total : h->B;
@@ -1082,7 +1098,7 @@ static int enqueue(gnssacq_handle* h, const void* d_if, gnssacq_result* d_out = 
     } else if (h->l2x_clusters > 0) {
         CU(h->ops->launch_search_l2x(sa, h->l2x_clusters, s));
     } else {
-        CU(h->ops->launch_search(sa, h->P * h->B, s));
+        CU(h->ops->launch_search(sa, h->n_rows, s));
     }
     h->launches += 1;
     CU(cudaEventRecord(h->ev[3], s));
@@ -1186,10 +1202,54 @@ int gnssacq_shard_plan(const gnssacq_config* full, int32_t rank, int32_t world, 
     return GNSSACQ_OK;                     // bin_count == 0 (more shards than bins): that shard has no rows and no handle
 }
 
+// rows [first, first + count) of shard `rank` under the row-granular plan: the root's share is (1000 + extra) / 1000
+// of the others'; what is left goes to the others in equal parts, the first few taking one row more
+static void plan_rows_range(long long total, int rank, int world, int extra_permille, long long& first, long long& count) {
+    if (world == 1) { first = 0; count = total; return; }
+    const long long wr = 1000 + extra_permille, wo = 1000;
+    long long root = (total * wr + (wr + (world - 1) * wo) / 2) / (wr + (world - 1) * wo);
+    if (root > total) root = total;
+    if (root < 1 && total > 0) root = 1;                     // the root always owns rows (it runs K4)
+    const long long rest = total - root, q = rest / (world - 1), rem = rest % (world - 1);
+    if (rank == 0) { first = 0; count = root; return; }
+    const long long r = rank - 1;
+    first = root + r * q + (r < rem ? r : rem);
+    count = q + (r < rem ? 1 : 0);
+}
+int gnssacq_shard_plan_rows(const gnssacq_config* full, int32_t rank, int32_t world, int32_t root_extra_permille,
+                            gnssacq_config* mine, gnssacq_shard* sh) {
+    std::string why;
+    if (!full || !mine || !sh || world < 1 || world > 62 || rank < 0 || rank >= world) return GNSSACQ_ERR_INVALID_ARG;
+    if (root_extra_permille <= -1000 || root_extra_permille > 100000) return fail(nullptr, GNSSACQ_ERR_INVALID_ARG, "root_extra_permille out of range");
+    if (int rc = validate(full, why)) return fail(nullptr, rc, why);
+    if (full->bin_count != 0 || full->row_count != 0) return fail(nullptr, GNSSACQ_ERR_INVALID_ARG, "shard_plan_rows wants the full grid (bin_count = row_count = 0)");
+    std::memset(sh, 0, sizeof *sh);
+    sh->rank = rank;
+    sh->world = world;
+    sh->n_prn_total = full->n_prn;
+    for (int i = 0; i < full->n_prn; ++i) sh->prn_total[i] = full->prn[i];
+    sh->freq_num_total = full->freq_num;
+    sh->prn_first = 0;
+    sh->prn_count = full->n_prn;
+    sh->bin_first = 0;
+    sh->bin_count = full->freq_num;
+    sh->plan_rows = 1;
+    sh->root_extra_permille = root_extra_permille;
+    long long first, count;
+    plan_rows_range((long long)full->n_prn * full->freq_num, rank, world, root_extra_permille, first, count);
+    sh->row_first = (int32_t)first;
+    sh->row_count = (int32_t)count;          // 0 (more shards than rows): that shard has no rows and no handle
+    *mine = *full;
+    mine->row_first = count > 0 ? sh->row_first : 0;
+    mine->row_count = sh->row_count;
+    return GNSSACQ_OK;
+}
+
 static int xchg_common(gnssacq_handle* h, const gnssacq_shard* sh) {
     if (!h || !sh) return fail(h, GNSSACQ_ERR_INVALID_ARG, "NULL argument");
     if (h->xc.on) return fail(h, GNSSACQ_ERR_STATE, "exchange already set up on this handle");
-    if (sh->prn_count != h->P || sh->bin_count != h->B || sh->bin_first != h->bin0 || sh->freq_num_total != h->B_full)
+    if (sh->prn_count != h->P || sh->bin_count != h->B || sh->bin_first != h->bin0 || sh->freq_num_total != h->B_full ||
+        (sh->plan_rows ? (sh->row_first != h->row0 || sh->row_count != h->n_rows) : (h->n_rows != h->P * h->B)))
         return fail(h, GNSSACQ_ERR_INVALID_ARG, "shard does not describe this handle (use gnssacq_shard_plan's config)");
     if (!h->d_comb) return fail(h, GNSSACQ_ERR_STATE, "the multi-GPU exchange needs the comb-row K1");
     CU(cudaSetDevice(h->device));
@@ -1291,7 +1351,19 @@ int gnssacq_xchg_finish(gnssacq_handle* h) {
     auto& xc = h->xc;
     CU(cudaEventRecord(xc.ev_c, s));
     if (xc.sh.world > 1) {
-        xchg_wait_kernel<<<1, 64, 0, s>>>(xc.flags + 1, xc.sh.world, xc.sh.n_prn_total, xc.sh.freq_num_total, xc.epoch, xc.flags + 63);
+        unsigned long long has_rows = 0;
+        for (int r = 1; r < xc.sh.world; ++r) {
+            bool has;
+            if (xc.sh.plan_rows) {
+                long long first, count;
+                plan_rows_range((long long)xc.sh.n_prn_total * xc.sh.freq_num_total, r, xc.sh.world, xc.sh.root_extra_permille, first, count);
+                has = count > 0;
+            } else {
+                has = xc.sh.n_prn_total >= xc.sh.world || xc.sh.freq_num_total / xc.sh.world > 0 || r < xc.sh.freq_num_total % xc.sh.world;
+            }
+            if (has) has_rows |= 1ull << r;
+        }
+        xchg_wait_kernel<<<1, 64, 0, s>>>(xc.flags + 1, xc.sh.world, has_rows, xc.epoch, xc.flags + 63);
         CU(cudaGetLastError());
         h->launches += 1;
     }

@@ -43,6 +43,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("cluster_ctas", C.c_int32), ("threads", C.c_int32),
         ("keep_surface", C.c_int32), ("exchange", C.c_int32), ("work_split", C.c_int32),
         ("bin_first", C.c_int32), ("bin_count", C.c_int32),
+        ("row_first", C.c_int32), ("row_count", C.c_int32),
     ]
 
 
@@ -99,7 +100,13 @@ class Shard(C.Structure):
         ("rank", C.c_int32), ("world", C.c_int32), ("n_prn_total", C.c_int32),
         ("prn_total", C.c_int32 * GNSSACQ_MAX_PRN), ("freq_num_total", C.c_int32),
         ("prn_first", C.c_int32), ("prn_count", C.c_int32), ("bin_first", C.c_int32), ("bin_count", C.c_int32),
+        ("row_first", C.c_int32), ("row_count", C.c_int32), ("plan_rows", C.c_int32), ("root_extra_permille", C.c_int32),
     ]
+
+    @property
+    def n_rows(self) -> int:
+        """(PRN, bin) rows this shard searches."""
+        return self.row_count if self.plan_rows else self.prn_count * self.bin_count
 
 
 EXPORTS = (
@@ -109,7 +116,7 @@ EXPORTS = (
     "gnssacq_ca_code", "gnssacq_code_replica", "gnssacq_read_surface", "gnssacq_fft_forward", "gnssacq_fp32_peak_tflops", "gnssacq_fine_frequency",
     "gnssacq_search_multi", "gnssacq_sweep", "gnssacq_sweep_file", "gnssacq_track_load", "gnssacq_correlate",
     "gnssacq_loop_params_default", "gnssacq_track",
-    "gnssacq_shard_plan", "gnssacq_xchg_root", "gnssacq_xchg_attach", "gnssacq_xchg_attach_local",
+    "gnssacq_shard_plan", "gnssacq_shard_plan_rows", "gnssacq_xchg_root", "gnssacq_xchg_attach", "gnssacq_xchg_attach_local",
     "gnssacq_xchg_if_buffer", "gnssacq_xchg_enqueue", "gnssacq_xchg_finish", "gnssacq_xchg_fetch",
 )
 
@@ -148,6 +155,7 @@ def _load() -> C.CDLL:
     lib.gnssacq_sweep.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_size_t, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_sweep_file.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(Result), C.POINTER(Stats)]
     lib.gnssacq_shard_plan.argtypes = [C.POINTER(Config), C.c_int32, C.c_int32, C.POINTER(Config), C.POINTER(Shard)]
+    lib.gnssacq_shard_plan_rows.argtypes = [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, C.POINTER(Config), C.POINTER(Shard)]
     lib.gnssacq_xchg_root.argtypes = [vp, C.POINTER(Shard), vp]
     lib.gnssacq_xchg_attach.argtypes = [vp, C.POINTER(Shard), vp]
     lib.gnssacq_xchg_attach_local.argtypes = [vp, C.POINTER(Shard), vp]
@@ -178,7 +186,7 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
                 freq_num: Optional[int] = None, noncoh_blocks=20, coh_ms=1,
                 prns: Sequence[int] = tuple(range(1, 33)), snr_threshold_db=12.0, device=-1,
                 cluster_ctas=0, threads=0, keep_surface=False, exchange=0, work_split=0,
-                bin_first=0, bin_count=0) -> Config:
+                bin_first=0, bin_count=0, row_first=0, row_count=0) -> Config:
     cfg = default_config()
     cfg.fs_hz, cfg.if_hz, cfg.code_hz = fs_hz, if_hz, code_hz
     cfg.samples_per_ms = int(samples_per_ms if samples_per_ms else np.ceil(fs_hz * 1e-3))
@@ -198,6 +206,7 @@ def make_config(*, fs_hz=58e6, if_hz=4.58e6, code_hz=1.023e6, samples_per_ms: Op
     cfg.exchange = int(exchange)
     cfg.work_split = int(work_split)
     cfg.bin_first, cfg.bin_count = int(bin_first), int(bin_count)
+    cfg.row_first, cfg.row_count = int(row_first), int(row_count)
     return cfg
 
 
@@ -206,6 +215,16 @@ def shard_plan(cfg: Config, rank: int, world: int):
     PRNs and a range of Doppler bins; a shard with ``bin_count == 0`` has no rows (more shards than bins)."""
     mine, sh = Config(), Shard()
     rc = lib.gnssacq_shard_plan(C.byref(cfg), rank, world, C.byref(mine), C.byref(sh))
+    if rc:
+        raise GnssAcqError(rc, (lib.gnssacq_last_error(None) or b"").decode())
+    return mine, sh
+
+
+def shard_plan_rows(cfg: Config, rank: int, world: int, root_extra_permille: int = 0):
+    """gnssacq_shard_plan_rows: every shard keeps all PRNs and takes a contiguous range of the (bin-major) rows; the
+    root's share is (1000 + root_extra_permille) / 1000 of the others'.  ``row_count == 0``: no rows, no handle."""
+    mine, sh = Config(), Shard()
+    rc = lib.gnssacq_shard_plan_rows(C.byref(cfg), rank, world, int(root_extra_permille), C.byref(mine), C.byref(sh))
     if rc:
         raise GnssAcqError(rc, (lib.gnssacq_last_error(None) or b"").decode())
     return mine, sh

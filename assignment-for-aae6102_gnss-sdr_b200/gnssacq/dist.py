@@ -65,17 +65,34 @@ class PeerShard:
     there are fewer PRNs than GPUs (then the Doppler bins are split).  `torch.distributed` is used once, to
     hand rank 0's CUDA IPC handle to the other processes.  No CPU fallback."""
 
-    def __init__(self, cfg_full: api.Config, rank: int, world: int, device: int, dist=None):
+    def __init__(self, cfg_full: api.Config, rank: int, world: int, device: int, dist=None,
+                 plan: str = "prn", root_extra_permille: int = 0):
+        """plan "prn": gnssacq_shard_plan (whole PRNs per shard, or bin ranges when there are fewer PRNs than shards);
+        plan "rows": gnssacq_shard_plan_rows (contiguous row ranges, the root's share weighted by
+        `root_extra_permille`; see rebalance())."""
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
         self._dist = dist
+        self._device = device
         torch.cuda.set_device(device)
-        full = api.Config.from_buffer_copy(bytes(cfg_full))
-        full.device = device
-        mine, self.shard = api.shard_plan(full, rank, world)
+        self._full = api.Config.from_buffer_copy(bytes(cfg_full))
+        self._full.device = device
+        self.plan = plan
+        self.root_extra_permille = int(root_extra_permille)
+        self.searcher = None
+        self._build()
+
+    def _build(self) -> None:
+        full, rank, world, dist = self._full, self.rank, self.world, self._dist
+        if self.plan == "rows":
+            mine, self.shard = api.shard_plan_rows(full, rank, world, self.root_extra_permille)
+        elif self.plan == "prn":
+            mine, self.shard = api.shard_plan(full, rank, world)
+        else:
+            raise ValueError(f"unknown shard plan {self.plan!r}")
         self.n_prn_total = self.shard.n_prn_total
-        self.rows_local = self.shard.prn_count * self.shard.bin_count
+        self.rows_local = self.shard.n_rows
         self.searcher = api.Searcher(mine) if self.rows_local > 0 else None
         self.if_bytes = int(api.lib.gnssacq_if_bytes(C.byref(full)))
         ipc = [None]
@@ -88,6 +105,62 @@ class PeerShard:
         if rank != 0 and self.searcher:
             self.searcher.xchg_attach(self.shard, ipc[0])
         self.d_if_ptr = self.searcher.xchg_if_buffer() if rank == 0 else 0
+
+    def rebalance(self, steps: int = 12, host_if=None) -> int:
+        """Level the finish times of the shards (plan "rows" only).  The other shards start every step later than
+        the root by the time the IF block takes to reach them, so with equal shares the root idles at the end of
+        each step (gnssacq_stats.gather_wait_ms).  Runs `steps` steps, reads on the root how long it waited relative
+        to its own search, moves that share of the rows from the others to the root, and rebuilds the handles of
+        every rank with the new plan.  Set-up work (one more create per rank): call it once, outside any timed
+        region, with the IF block already in the exchange buffer (upload()) or passed as `host_if`.  Collective:
+        every rank must call it.  Returns the new root_extra_permille.  Results do not depend on the plan."""
+        if self.plan != "rows" or self.world == 1:
+            return self.root_extra_permille
+        torch, dist = self.torch, self._dist
+        waits, searches = [], []
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            self.enqueue(host_if)
+            self.fetch()
+            if self.rank == 0:
+                st = self.searcher.last_stats
+                waits.append(st.gather_wait_ms)
+                searches.append(st.search_ms)
+        msg = [None]
+        if self.rank == 0:
+            # root idles `wait` per `search` of its own rows: give it that many more (its rows' time grows by
+            # wait * (world-1)/world, everybody else's shrinks by wait/world -> equal finish).  Medians: one slow
+            # step (a late launch on some rank) must not skew the plan.
+            wait = sorted(waits)[len(waits) // 2]
+            search = sorted(searches)[len(searches) // 2]
+            wait = max(wait - 0.003, 0.0)                      # the wait kernel's own latency when nobody is late
+            frac = (wait / search) if search > 0 else 0.0
+            g = self.world
+            # weights: root = 1 + e, others 1.  Root share now: (1+e0)/(g+e0); wanted: that * (1 + frac*(g-1)/g)
+            e0 = self.root_extra_permille / 1000.0
+            share = (1 + e0) / (g + e0) * (1 + frac * (g - 1) / g)
+            share = min(share, 0.9)
+            e1 = (share * g - 1) / (1 - share)
+            msg[0] = (int(round(1000 * e1)),)
+        dist.broadcast_object_list(msg, src=0)
+        new_extra = msg[0][0]
+        if new_extra != self.root_extra_permille:
+            saved = self._saved_if()
+            self.close(_final=False)
+            self.root_extra_permille = new_extra
+            self._build()
+            if self.rank == 0 and saved is not None:
+                self._copy_into_if(saved)
+                torch.cuda.synchronize()
+        return self.root_extra_permille
+
+    def _saved_if(self):
+        """rank 0: a device copy of the exchange buffer's IF block (it moves with the handle)."""
+        if self.rank != 0 or not self.d_if_ptr:
+            return None
+        arr = _DevArray(self.d_if_ptr, self.if_bytes)
+        return self.torch.as_tensor(arr, device="cuda").clone()
 
     def bind_stream(self) -> None:
         if self.searcher:
@@ -122,7 +195,7 @@ class PeerShard:
             return []
         return self.searcher.xchg_fetch(rows=(self.rank == 0))
 
-    def close(self) -> None:
+    def close(self, _final: bool = True) -> None:
         """The other ranks unmap the root's exchange block BEFORE the root frees it."""
         if self.rank != 0 and self.searcher:
             self.searcher.close()
@@ -147,7 +220,7 @@ class LocalMultiGpu:
     torchrun).  If several shards share a device (tests on a one-GPU box), the steps are serialised with host
     syncs, because kernels of different shards that wait for one another must not share a GPU."""
 
-    def __init__(self, cfg_full: api.Config, devices: Sequence[int]):
+    def __init__(self, cfg_full: api.Config, devices: Sequence[int], plan: str = "prn", root_extra_permille: int = 0):
         self.world = len(devices)
         self.serial = len(set(devices)) < len(devices)
         self.searchers: List[api.Searcher] = []
@@ -155,9 +228,12 @@ class LocalMultiGpu:
         for r, dev in enumerate(devices):
             full = api.Config.from_buffer_copy(bytes(cfg_full))
             full.device = dev
-            mine, sh = api.shard_plan(full, r, self.world)
+            if plan == "rows":
+                mine, sh = api.shard_plan_rows(full, r, self.world, root_extra_permille)
+            else:
+                mine, sh = api.shard_plan(full, r, self.world)
             self.shards.append(sh)
-            self.searchers.append(api.Searcher(mine) if sh.prn_count * sh.bin_count > 0 else None)
+            self.searchers.append(api.Searcher(mine) if sh.n_rows > 0 else None)
         root = self.searchers[0]
         root.xchg_root(self.shards[0])
         for s, sh in zip(self.searchers[1:], self.shards[1:]):

@@ -322,10 +322,15 @@ def run_gpu(args, cfg):
     peer = args.xchg == "peer"
     if peer:
         # exchange through peer memory (gnssacq_xchg_*): no NCCL inside a step.  Same call shape as CudaShard below.
-        ps = PeerShard(factory(PRNS, local), rank, world, local, dist if world > 1 else None)
+        # plan "rows" (default when there is more than one GPU): contiguous row ranges, the root's share weighted so
+        # that all shards FINISH together (the others start later by the IF pull) -- calibrated once after the warm-up
+        plan = args.plan if args.plan != "auto" else ("rows" if world > 1 else "prn")
+        ps = PeerShard(factory(PRNS, local), rank, world, local, dist if world > 1 else None, plan=plan,
+                       root_extra_permille=args.root_extra if args.root_extra is not None else 0)
 
         class _Shard:
             searcher, n_local, max_rows = ps.searcher, ps.shard.prn_count, (len(PRNS) + world - 1) // world
+            rows_local = ps.rows_local
 
             @staticmethod
             def enqueue(_d, h_if=None):
@@ -340,7 +345,9 @@ def run_gpu(args, cfg):
         shard = _Shard
         shard.load(h_if)
     else:
+        plan = "prn"
         shard = CudaShard(factory, PRNS, rank, world, local)
+        shard.rows_local = shard.n_local * cfg["bins"]
         shard.bind_stream()
         shard.d_if.copy_(h_if)
         shard.load = lambda t: shard.d_if.copy_(t)
@@ -356,6 +363,15 @@ def run_gpu(args, cfg):
     for _ in range(max(args.warmup, 3)):
         shard.enqueue(d)
     rows = shard.fetch()
+    root_extra = None
+    if peer and plan == "rows" and world > 1:
+        if args.root_extra is None:
+            ps.rebalance()                                  # set-up: weighs the root's share from the measured waits
+            shard.searcher, shard.rows_local = ps.searcher, ps.rows_local
+            for _ in range(3):
+                shard.enqueue(d)
+            rows = shard.fetch()
+        root_extra = ps.root_extra_permille
 
     # ---- timed region 1: device-resident input, per-step CUDA events, L2 flushed between steps ----
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -448,7 +464,7 @@ def run_gpu(args, cfg):
     if rank == 0:
         n_local = shard.n_local
         nb = st.n_bases
-        w_search = n_local * cfg["bins"] * cfg["k"] * w_unit(cfg["n"])          # flops of ONE search_kernel launch
+        w_search = shard.rows_local * cfg["k"] * w_unit(cfg["n"])               # flops of ONE search_kernel launch (rank 0's rows)
         k2 = sum(k2_ms) / len(k2_ms)
         try:
             fp32_peak = api.fp32_peak_tflops(local)
@@ -475,7 +491,9 @@ def run_gpu(args, cfg):
             "run": {   "forward_bases": nb, "engine": {"cluster_ctas": variant[0], "threads": variant[1], "exchange": {1: "dsmem", 2: "l2+clusters", 3: "l2+coop-groups"}.get(st.exchange),
                                   "resident_clusters": st.resident_clusters,
                                   "work_split": {1: "whole rows", 2: "block-granular tail"}.get(st.work_split)},
-                       "sharding": f"PRN-major, {n_local} PRNs on rank 0",
+                       "sharding": (f"PRN-major, {n_local} PRNs on rank 0" if plan == "prn" else
+                                    f"row ranges (gnssacq_shard_plan_rows), {shard.rows_local} of {len(PRNS) * cfg['bins']} rows on rank 0, "
+                                    f"root weight 1 + {root_extra}/1000 " + ("calibrated by PeerShard.rebalance() after the warm-up" if args.root_extra is None else "as given")),
                        "exchange_between_gpus": ("peer memory (CUDA IPC over NVLink): K1a pulls the IF block from rank 0, K2 stores its "
                                                  "candidates into rank 0's table, K4 on rank 0; no NCCL call inside a step" if peer else
                                                  "NCCL broadcast of the IF block + all_gather of the result rows") if world > 1 else "none (one GPU)",
@@ -609,6 +627,11 @@ def main():
     ap.add_argument("--exchange", type=int, default=0, help="0 auto, 1 DSMEM, 2 L2-resident exchange buffer")
     ap.add_argument("--xchg", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU exchange: peer memory (gnssacq_xchg_*, default) or the r01 NCCL broadcast + all-gather")
+    ap.add_argument("--plan", default="auto", choices=["auto", "prn", "rows"],
+                    help="multi-GPU shards (peer exchange): whole PRNs / bin ranges (gnssacq_shard_plan) or weighted row ranges "
+                         "(gnssacq_shard_plan_rows); auto = rows when there is more than one GPU")
+    ap.add_argument("--root-extra", type=int, default=None,
+                    help="plan rows: the root's extra share in 1/1000 of an equal share (default: calibrate after the warm-up)")
     ap.add_argument("--sweep-shard", default="grid", choices=["grid", "epochs"],
                     help="config 4 on N GPUs: shard every acquisition's PRN x Doppler grid (default, BASELINE's wording) or deal out the epochs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -75,6 +75,11 @@ typedef struct gnssacq_config {
     int32_t bin_count;        /* (a rank's shard when there are fewer PRNs than GPUs); 0 = all freq_num
                                  bins.  The forward transforms are planned on the FULL grid, so a sub-range produces
                                  bit for bit the candidates the full search has for those bins */
+    int32_t row_first;        /* this handle searches rows [row_first, row_first + row_count) of its n_prn x bins grid, */
+    int32_t row_count;        /* rows counted bin-major (row = bin * n_prn + prn index: the order the search kernel walks
+                                 them).  0 = all rows.  A shard of gnssacq_shard_plan_rows: any share of the grid, to the
+                                 row -- a PRN whose bins are spread over several shards is finished on the root
+                                 (gnssacq_xchg_*); used alone, such a handle reports the best of the rows it owns */
 } gnssacq_config;
 
 /* One PRN's coarse-search outcome (acquisition.m:62-74); returned for every PRN, acquired or not. */
@@ -194,10 +199,22 @@ typedef struct gnssacq_shard {
     int32_t freq_num_total;
     int32_t prn_first, prn_count;         /* this shard's rows: PRNs [prn_first, +prn_count) x bins [bin_first, +bin_count) */
     int32_t bin_first, bin_count;
+    int32_t row_first, row_count;         /* gnssacq_shard_plan_rows: rows [row_first, +row_count) of that grid, bin-major
+                                             (row_count = 0 with plan_rows = 0: the whole rectangle) */
+    int32_t plan_rows;                    /* 1 = made by gnssacq_shard_plan_rows */
+    int32_t root_extra_permille;          /* its weight argument (the root recomputes the other shards' shares from it) */
 } gnssacq_shard;
 #define GNSSACQ_IPC_BYTES 64
 /* full config + (rank, world) -> this shard's config (`mine`: PRN subset and bin range filled in) and its place */
 int gnssacq_shard_plan(const gnssacq_config* full, int32_t rank, int32_t world, gnssacq_config* mine, gnssacq_shard* shard);
+/* Row-granular plan: the n_prn x freq_num rows, in the bin-major order the search kernel walks them, are cut into
+ * `world` contiguous ranges; every shard keeps all PRNs (their code spectra are cached per handle) and computes only its
+ * rows.  The root's range is (1000 + root_extra_permille) / 1000 times the others': the other shards start a step later
+ * than the root by the time the IF block needs to reach them (gnssacq_stats.if_pull_ms), so equal shares leave the
+ * root waiting at the end of every step (gnssacq_stats.gather_wait_ms); a few per cent more rows on the root level the
+ * finish times.  root_extra_permille may be negative (> -1000).  Result rows do not depend on the plan. */
+int gnssacq_shard_plan_rows(const gnssacq_config* full, int32_t rank, int32_t world, int32_t root_extra_permille,
+                            gnssacq_config* mine, gnssacq_shard* shard);
 /* root only: allocate the exchange block; ipc_out (GNSSACQ_IPC_BYTES, may be NULL) receives the handle other
  * PROCESSES open with gnssacq_xchg_attach */
 int gnssacq_xchg_root(gnssacq_handle* root, const gnssacq_shard* shard, void* ipc_out);

@@ -114,6 +114,38 @@ def test_shard_plan_tiles_the_grid():
         api.shard_plan(gnssacq.make_config(prns=[1]), 2, 2)
 
 
+def test_shard_plan_rows_tiles_the_grid():
+    """gnssacq_shard_plan_rows (host only): contiguous ranges of the bin-major row list, every row exactly once; the
+    root's share follows its weight, the other shards differ by at most one row; a shard may end up empty."""
+    for prns, bins, world, extra in [(list(range(1, 33)), 41, 8, 0), (list(range(1, 33)), 41, 8, 45), (list(range(1, 33)), 41, 5, -200),
+                                     ([7], 41, 8, 100), ([3, 9, 30], 2001, 8, 10), ([5], 3, 8, 0), ([5, 6], 1, 4, 300),
+                                     (list(range(1, 33)), 41, 1, 70)]:
+        cfg = gnssacq.make_config(prns=prns, freq_num=bins, freq_step_hz=500.0)
+        total = len(prns) * bins
+        nxt, sizes = 0, []
+        for r in range(world):
+            mine, sh = api.shard_plan_rows(cfg, r, world, extra)
+            assert (sh.rank, sh.world, sh.n_prn_total, sh.freq_num_total, sh.plan_rows, sh.root_extra_permille) == (r, world, len(prns), bins, 1, extra)
+            assert list(mine.prn[: mine.n_prn]) == prns and (mine.bin_first, mine.bin_count) == (0, 0)
+            assert sh.n_rows == sh.row_count == mine.row_count
+            if sh.row_count:
+                assert sh.row_first == nxt == mine.row_first
+            nxt += sh.row_count
+            sizes.append(sh.row_count)
+        assert nxt == total
+        assert sizes[0] >= 1
+        if world > 1:
+            others = sizes[1:]
+            assert max(others) - min(others) <= 1
+            want_root = total * (1000 + extra) / (1000 * world + extra)
+            assert abs(sizes[0] - max(1.0, want_root)) <= 1.0
+    with pytest.raises(gnssacq.GnssAcqError):
+        api.shard_plan_rows(gnssacq.make_config(prns=[1]), 0, 2, -1000)
+    bad = gnssacq.make_config(prns=[1, 2], row_first=80, row_count=10)      # 2 x 41 grid has 82 rows
+    with pytest.raises(gnssacq.GnssAcqError):
+        api.shard_plan(bad, 0, 1)
+
+
 def _cand_of_rows(surface, w):
     """(peak, first lag, sum of squares, windowed sum of squares) of every bin row: what K2/K3 emit per row."""
     out = []

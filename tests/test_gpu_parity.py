@@ -447,6 +447,55 @@ def test_peer_memory_exchange_shards_give_the_single_gpu_bytes(prns, world):
     assert_rows_match(got, oracle_rows(raw_b, file, signal, acq, prns), what=f"xchg world={world}")
 
 
+@pytest.mark.parametrize("prns,world,extra", [([1, 3, 7, 16, 22, 30], 2, 0), ([1, 3, 7, 16, 22, 30], 4, 60), ([1, 3, 7, 16, 22, 30], 8, -300),
+                                              ([7], 4, 250), ([3, 22], 5, 0), ([7], 48, 0)])
+def test_row_range_shards_give_the_single_gpu_bytes(prns, world, extra):
+    """gnssacq_shard_plan_rows: the (PRN, bin) rows cut into `world` contiguous ranges of the kernel's own bin-major
+    order, the root's share weighted -- a PRN's bins end up on several shards, the root's K4 sees the full table: the
+    rows are byte for byte the single-handle search's, whatever the weight."""
+    from gnssacq.dist import LocalMultiGpu
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=3)
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 3)
+    cfg = cfg_from(file, signal, acq, prns)
+    with api.Searcher(cfg) as s:
+        want = [bytes(r) for r in s.search(raw_b)]
+    with LocalMultiGpu(cfg, [0] * world, plan="rows", root_extra_permille=extra) as m:
+        assert sum(sh.n_rows for sh in m.shards) == len(prns) * cfg.freq_num
+        got = m.search(raw_b)
+        again = m.search(raw_b)
+    assert [bytes(r) for r in got] == want
+    assert [bytes(r) for r in again] == want
+
+
+def test_row_range_handle_alone_and_full_size():
+    """A handle with config.row_first / row_count used alone reports, per PRN, the best of the rows it owns (cells it
+    never writes cannot win); and at the Urban front end's size (cooperative kernel, block-granular tail) three row
+    ranges with a heavy root reproduce the single-handle bytes."""
+    from gnssacq.dist import LocalMultiGpu
+    fs, if_hz, n = 6e6, 1.25e6, 6000
+    file, signal, acq = structs(fs, if_hz, datalen=2)
+    raw_b = synth_if(small_spec(fs, if_hz, n), 0, 2)
+    prns = [3, 7]
+    with api.Searcher(cfg_from(file, signal, acq, prns)) as s:
+        full = s.search(raw_b)
+    b = full[0].doppler_bin
+    cfg = cfg_from(file, signal, acq, prns)
+    cfg.row_first, cfg.row_count = 2 * b, 1                           # exactly PRN 3's winning row (row = bin * n_prn + index)
+    with api.Searcher(cfg) as s:
+        part = s.search(raw_b)
+    assert bytes(part[0]) == bytes(full[0])
+    assert part[1].peak == -1.0 and not part[1].acquired            # PRN 7 owns no row here
+    from gnssacq.synth import urban_recording
+    raw_u = urban_recording().read(0, 4)
+    ucfg = gnssacq.make_config(fs_hz=26e6, if_hz=0.0, prns=[1, 3, 11], noncoh_blocks=4)
+    with api.Searcher(ucfg) as s:
+        want = [bytes(r) for r in s.search(raw_u)]
+    with LocalMultiGpu(ucfg, [0, 0, 0], plan="rows", root_extra_permille=400) as m:
+        got = m.search(raw_u)
+    assert [bytes(r) for r in got] == want
+
+
 def test_bin_range_handle_alone():
     """A handle that owns bins [b0, b0+n) of the grid (config.bin_first / bin_count) reports its winner in FULL-grid
     bin indices and produces the full search's candidates for those bins (same forward bases)."""
