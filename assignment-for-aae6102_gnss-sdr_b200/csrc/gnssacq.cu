@@ -1000,6 +1000,9 @@ extern "C" int gnssacq_debug_timeline(unsigned long long* out /*[16*16*32]*/) {
 // overlaps the DMA of chunk i (one chunk of latency instead of the sum of both copies).  The caller's buffer is
 // free again when this returns.
 static int stage_and_upload(gnssacq_handle* h, void* d_dst, const void* host_src, cudaStream_t s) {
+    // (Helper threads for the host copy were built and measured in r02: three helpers claiming 128 kB pieces next to the
+    // caller's thread made the upload of the 2.32 MB block SLOWER, 0.30 ms against 0.185 ms, on the 16-core host of the
+    // GPU box -- waking sleeping threads costs more than the 0.1 ms they could save.  profiles/r02/time_e2e_staging_helpers_v16.txt)
     constexpr size_t kChunk = 512 << 10;
     const unsigned char* src = static_cast<const unsigned char*>(host_src);
     unsigned char* pin = static_cast<unsigned char*>(h->h_if);

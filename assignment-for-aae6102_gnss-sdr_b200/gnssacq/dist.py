@@ -52,6 +52,20 @@ def merge_candidates(cands, n_samples: int, w: int, fmin: float, fstep: float, t
     return cp, fbin, fmin + fstep * fbin, g, noise, snr, bool(snr >= thr)
 
 
+def root_extra_for_wait(extra_permille: int, wait_ms: float, search_ms: float, world: int) -> int:
+    """The root's weight (gnssacq_shard_plan_rows' root_extra_permille) that levels the finish times, given that with
+    the weight `extra_permille` the root waited `wait_ms` for the other shards after `search_ms` of its own search.
+    Moving x rows to the root costs it x row times and saves every other shard x/(world-1): equal finish at
+    x = wait/T_row * (world-1)/world, i.e. the root's share grows by the factor 1 + (wait/search)(world-1)/world.
+    (The step gets shorter by wait/world, not by wait: only ONE GPU was idle.)"""
+    if world <= 1 or search_ms <= 0:
+        return int(extra_permille)
+    e0 = extra_permille / 1000.0
+    share = (1 + e0) / (world + e0) * (1 + max(wait_ms, 0.0) / search_ms * (world - 1) / world)
+    share = min(share, 0.9)
+    return int(round(1000 * (share * world - 1) / (1 - share)))
+
+
 def rows_from_bytes(buf: bytes) -> List[api.Result]:
     n = len(buf) // ROW_BYTES
     return list((api.Result * n).from_buffer_copy(buf[: n * ROW_BYTES]))
@@ -135,14 +149,7 @@ class PeerShard:
             wait = sorted(waits)[len(waits) // 2]
             search = sorted(searches)[len(searches) // 2]
             wait = max(wait - 0.003, 0.0)                      # the wait kernel's own latency when nobody is late
-            frac = (wait / search) if search > 0 else 0.0
-            g = self.world
-            # weights: root = 1 + e, others 1.  Root share now: (1+e0)/(g+e0); wanted: that * (1 + frac*(g-1)/g)
-            e0 = self.root_extra_permille / 1000.0
-            share = (1 + e0) / (g + e0) * (1 + frac * (g - 1) / g)
-            share = min(share, 0.9)
-            e1 = (share * g - 1) / (1 - share)
-            msg[0] = (int(round(1000 * e1)),)
+            msg[0] = (root_extra_for_wait(self.root_extra_permille, wait, search, self.world),)
         dist.broadcast_object_list(msg, src=0)
         new_extra = msg[0][0]
         if new_extra != self.root_extra_permille:

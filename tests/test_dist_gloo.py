@@ -146,6 +146,27 @@ def test_shard_plan_rows_tiles_the_grid():
         api.shard_plan(bad, 0, 1)
 
 
+def test_root_weight_from_the_measured_wait():
+    """dist.root_extra_for_wait (PeerShard.rebalance's arithmetic): no wait keeps the weight; a wait of w after a search
+    of s moves w/s * (G-1)/G of the root's rows' worth to the root; planning with the new weight and a linear cost
+    model (rows x row time, the others delayed by a fixed amount) levels the finish times to within one row."""
+    from gnssacq.dist import root_extra_for_wait
+    assert root_extra_for_wait(0, 0.0, 1.0, 8) == 0
+    assert root_extra_for_wait(70, 0.0, 1.0, 8) == 70
+    assert root_extra_for_wait(0, 0.04, 0.9, 1) == 0
+    cfg = gnssacq.make_config(prns=list(range(1, 33)), freq_num=41, freq_step_hz=500.0)
+    t_row, delay = 5.5e-3, 40e-3                                             # ms per row, ms the others start late
+    for world in (2, 4, 8):
+        rows0 = [api.shard_plan_rows(cfg, r, world, 0)[1].row_count for r in range(world)]
+        wait = delay + (max(rows0[1:]) - rows0[0]) * t_row                   # what the root measures with equal shares
+        extra = root_extra_for_wait(0, wait, rows0[0] * t_row, world)
+        rows1 = [api.shard_plan_rows(cfg, r, world, extra)[1].row_count for r in range(world)]
+        assert sum(rows1) == 32 * 41 and rows1[0] > rows0[0]
+        finish_root, finish_others = rows1[0] * t_row, delay + max(rows1[1:]) * t_row
+        assert abs(finish_root - finish_others) <= 1.5 * t_row
+        assert max(finish_root, finish_others) <= delay + max(rows0[1:]) * t_row  # never longer (whole rows: not always shorter)
+
+
 def _cand_of_rows(surface, w):
     """(peak, first lag, sum of squares, windowed sum of squares) of every bin row: what K2/K3 emit per row."""
     out = []
