@@ -504,7 +504,7 @@ def run_gpu(args, cfg):
                            if world == 1 else f"{len(raws)} distinct windows cycled, one host window per step"} if sweep else {})},
             "roofline": {"bound": "fp32", "kernel": "search_kernel", "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
-                         "traffic_source": "dram__bytes_read+write of one search-kernel launch from the committed ncu --set full capture (profiles/r02/ncu_v14_search_c*.summary.txt via profiles/ncu_traffic.json); a bench run cannot sit under ncu, so this figure is not re-measured here",
+                         "traffic_source": "dram__bytes_read+write of one search-kernel launch from the committed ncu --set full capture (profiles/r02/ncu_v16_search_c*.summary.txt via profiles/ncu_traffic.json); a bench run cannot sit under ncu, so this figure is not re-measured here",
                          "peak_source": peak_src, "nominal_peak": 74.4,
                          "algorithmic_flops_per_launch": w_search, "kernel_ms": k2,
                          "wipeoff_fft_kernel_ms": sum(k1_ms) / len(k1_ms),
