@@ -15,6 +15,9 @@
 #include <string>
 #include <vector>
 #include <cooperative_groups.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/gnssacq.h"
 #include "gnss_internal.h"
@@ -938,7 +941,10 @@ int gnssacq_create(const gnssacq_config* cfg, gnssacq_handle** out) {
         if (by_blocks) CUC(cudaMalloc(&h->d_partial, (size_t)n * (h->K - 1) * ops->partial_bytes_per_group));
         CUC(cudaMalloc(&h->d_row_slots, (size_t)n * ops->R * sizeof(Candidate)));
     }
-    if (cfg->keep_surface) CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
+    if (cfg->keep_surface) {
+        CUC(cudaMalloc(&h->d_surface, (size_t)h->P * h->B * N * sizeof(float)));
+        if (h->n_rows < h->P * h->B) CUC(cudaMemset(h->d_surface, 0, (size_t)h->P * h->B * N * sizeof(float)));   // rows it never searches read as zeros
+    }
     CUC(cudaMallocHost(&h->h_if, h->if_bytes));
     CUC(cudaMallocHost(&h->h_res, h->P * sizeof(gnssacq_result)));
     // Every create-time copy goes on the handle's own (non-blocking) stream: a synchronous cudaMemcpy from
@@ -999,6 +1005,29 @@ extern "C" int gnssacq_debug_timeline(unsigned long long* out /*[16*16*32]*/) {
 // Pageable caller memory -> HBM through the handle's pinned staging buffer, in chunks: the host copy of chunk i+1
 // overlaps the DMA of chunk i (one chunk of latency instead of the sum of both copies).  The caller's buffer is
 // free again when this returns.
+// Host copy into the pinned staging buffer with non-temporal stores: the destination is only ever read by the DMA
+// engine, so it should neither be fetched into the cache first (read-for-ownership) nor evict the caller's data.
+static void copy_to_staging(unsigned char* dst, const unsigned char* src, size_t n) {
+#if defined(__x86_64__) && !defined(GNSS_EXPERIMENT_PLAIN_MEMCPY)
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+        }
+        if (i < n) std::memcpy(dst + i, src + i, n - i);
+        _mm_sfence();                                    // the streamed lines are globally visible before the DMA is queued
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
 static int stage_and_upload(gnssacq_handle* h, void* d_dst, const void* host_src, cudaStream_t s) {
     // (Helper threads for the host copy were built and measured in r02: three helpers claiming 128 kB pieces next to the
     // caller's thread made the upload of the 2.32 MB block SLOWER, 0.30 ms against 0.185 ms, on the 16-core host of the
@@ -1010,7 +1039,7 @@ static int stage_and_upload(gnssacq_handle* h, void* d_dst, const void* host_src
     else CU(cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming));
     for (size_t off = 0; off < h->if_bytes; off += kChunk) {
         const size_t n = std::min(kChunk, h->if_bytes - off);
-        std::memcpy(pin + off, src + off, n);
+        copy_to_staging(pin + off, src + off, n);
         CU(cudaMemcpyAsync(static_cast<unsigned char*>(d_dst) + off, pin + off, n, cudaMemcpyHostToDevice, s));
     }
     CU(cudaEventRecord(h->ev_upload, s));
