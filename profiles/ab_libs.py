@@ -18,7 +18,7 @@ for which in ("urban", "opensky"):
     spec, fs, if_hz = (urban_recording(), 26e6, 0.0) if which == "urban" else (opensky_recording(), 58e6, 4.58e6)
     raw = spec.read(0, 20)
     for n in prns:
-        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}), **({'threads': int(os.environ['AB_THREADS_' + which.upper()])} if os.environ.get('AB_THREADS_' + which.upper()) else {}))) as s:
+        with api.Searcher(gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=range(1, n + 1), **({'work_split': int(os.environ['AB_WORK_SPLIT'])} if os.environ.get('AB_WORK_SPLIT') else {}), **({'threads': int(os.environ['AB_THREADS_' + which.upper()].split('x')[-1]), 'cluster_ctas': int(os.environ['AB_THREADS_' + which.upper()].split('x')[0]) if 'x' in os.environ['AB_THREADS_' + which.upper()] else 0} if os.environ.get('AB_THREADS_' + which.upper()) else {}))) as s:
             best = 1e9
             for _ in range(8):
                 rows = s.search(raw)
