@@ -229,3 +229,64 @@ def test_world2_gloo_bin_split_merge_equals_single_search():
     ref = oracle_rows(raw, file, signal, acq, [7])[0]
     assert (cp, fbin, dop, acquired) == (ref.code_phase, ref.doppler_bin, ref.doppler_hz, ref.acquired)
     assert abs(peak - ref.peak) <= 1e-12 * ref.peak and abs(snr - ref.snr_db) <= 1e-9
+
+
+def _row_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import math
+    import oracle
+    from oracle.acquisition_ref import correlation_surface, samples_from_bytes
+    fs, if_hz, prns, bins = 6e6, 1.25e6, [3, 7], 7
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1500.0, freq_step=500.0, freq_num=bins)
+    n = int(signal.Sample)
+    raw = torch.frombuffer(bytearray(synth_if(small_spec(fs, if_hz, n), 0, 2)), dtype=torch.uint8).clone() \
+        if rank == 0 else torch.empty(n * 2 * 2, dtype=torch.uint8)
+    dist.broadcast(raw, src=0)
+    cfg = gnssacq.make_config(fs_hz=fs, if_hz=if_hz, prns=prns, freq_min_hz=-1500.0, freq_step_hz=500.0, freq_num=bins, noncoh_blocks=2)
+    mine, sh = api.shard_plan_rows(cfg, rank, world, 300)            # 14 rows: a heavy root (8) and one more shard (6)
+    assert sh.plan_rows == 1 and mine.n_prn == 2 and mine.row_count == sh.row_count
+    w = int(math.ceil(fs / 1.023e6))
+    x = samples_from_bytes(raw.numpy().tobytes(), 2, 1)
+    surf = {p: None for p in range(len(prns))}
+    mine_rows = []
+    for row in range(sh.row_first, sh.row_first + sh.row_count):    # row = bin * n_prn + prn index (the kernel's order)
+        b, p = divmod(row, len(prns))
+        if surf[p] is None:                                          # the oracle stands in for this rank's GPU
+            surf[p] = correlation_surface(x, signal, oracle.AcqParams(freqStep=500.0, freqMin=-1500.0, freqNum=bins, datalen=2), prns[p])
+        mine_rows.append((p, b, _cand_of_rows(surf[p][b: b + 1], w)[0]))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine_rows)
+    if rank == 0:
+        table = [[None] * bins for _ in prns]
+        for part in gathered:
+            for p, b, cand in part:
+                assert table[p][b] is None                           # every row exactly once
+                table[p][b] = cand
+        q.put([merge_candidates(table[p], n, w, -1500.0, 500.0) for p in range(len(prns))])
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_row_ranges_merge_equals_single_search():
+    """gnssacq_shard_plan_rows on two ranks with a weighted root: both PRNs have bins on both ranks; the per-row
+    candidates, gathered into the full table and merged with K4's rule, give the single-process oracle rows."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_row_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    fs, if_hz = 6e6, 1.25e6
+    file, signal, acq = structs(fs, if_hz, datalen=2, freq_min=-1500.0, freq_step=500.0, freq_num=7)
+    raw = synth_if(small_spec(fs, if_hz, int(signal.Sample)), 0, 2)
+    refs = oracle_rows(raw, file, signal, acq, [3, 7])
+    for (cp, fbin, dop, peak, noise, snr, acquired), ref in zip(merged, refs):
+        assert (cp, fbin, dop, acquired) == (ref.code_phase, ref.doppler_bin, ref.doppler_hz, ref.acquired)
+        assert abs(peak - ref.peak) <= 1e-12 * ref.peak and abs(snr - ref.snr_db) <= 1e-9
